@@ -1,0 +1,189 @@
+"""ctypes front end of the CPU oracle (oracle/liborc.so). TEST INFRASTRUCTURE:
+imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs."""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+MAX_P = 8
+
+MIS = dict(balance=0, power=1, weighted=2, optimal_clamped=3, optimal=4)
+LIGHT = dict(uniform=0, reservoir=1)
+POLY = dict(baseline=0, area_turk=1, projected_solid_angle=2, projected_solid_angle_biased=3, ltc_cp=4)
+
+
+def build(force=False):
+    lib = HERE / "liborc.so"
+    srcs = [HERE / n for n in ("risltc_oracle.c", "risltc_oracle_frame.inc", "risltc_oracle.h", "clip_rotation_table.h")]
+    if force or not lib.exists() or any(s.stat().st_mtime > lib.stat().st_mtime for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", str(HERE), "liborc.so"], env={**os.environ, "CC": "gcc"})
+    return lib
+
+
+class Variant(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("light_sampling", "polygon_technique", "mis_heuristic", "sample_count",
+                                          "light_samples", "fast_atan", "min_light_vertices", "max_light_vertices")]
+
+
+class Constants(C.Structure):
+    _fields_ = [("dequant_factor", C.c_float * 3), ("pad0", C.c_float), ("dequant_summand", C.c_float * 3),
+                ("error_factor", C.c_float), ("world_to_projection", (C.c_float * 4) * 4),
+                ("pixel_to_ray", (C.c_float * 4) * 3), ("camera_position", C.c_float * 3),
+                ("mis_visibility_estimate", C.c_float), ("viewport", C.c_uint32 * 2), ("cursor", C.c_int32 * 2),
+                ("exposure_factor", C.c_float), ("roughness_factor", C.c_float),
+                ("noise_resolution_mask", C.c_uint32 * 2), ("noise_texture_index_mask", C.c_uint32),
+                ("pad3", C.c_uint32 * 3), ("noise_random_numbers", C.c_uint32 * 4), ("ltc_constants", C.c_float * 8)]
+
+
+assert C.sizeof(Constants) == 256
+
+
+class Scene(C.Structure):
+    _fields_ = [("triangle_count", C.c_uint64), ("dequant_factor", C.c_float * 3), ("dequant_summand", C.c_float * 3),
+                ("positions", C.c_void_p), ("normals_uv", C.c_void_p), ("material_indices", C.c_void_p),
+                ("material_count", C.c_uint64), ("materials", C.c_void_p), ("light_count", C.c_uint32),
+                ("light_records", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
+                ("ltc_rgba16", C.c_void_p), ("ltc_rg16", C.c_void_p), ("bvh", C.c_void_p)]
+
+
+class PsaPolygon(C.Structure):
+    _fields_ = [("vertex_count", C.c_uint32), ("vertices", (C.c_float * 2) * MAX_P), ("ellipses", (C.c_float * 2) * MAX_P),
+                ("inner_ellipse_0", C.c_float * 2), ("sector_projected_solid_angles", C.c_float * MAX_P),
+                ("projected_solid_angle", C.c_float)]
+
+
+class Ltc(C.Structure):
+    _fields_ = [("world_to_shading", (C.c_float * 3) * 4), ("shading_to_cosine", (C.c_float * 3) * 3),
+                ("cosine_to_shading", (C.c_float * 3) * 3), ("albedo", C.c_float), ("determinant", C.c_float)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(build()))
+        _lib.orc_noise_next.restype = C.c_float
+        _lib.orc_calculate_ltc.restype = C.c_float
+        _lib.orc_render_frame.restype = C.c_uint64
+        _lib.orc_wang_random_number.restype = C.c_uint32
+        _lib.orc_noise_seed.restype = C.c_uint32
+        _lib.orc_clip_polygon.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def variant(light_sampling="reservoir", technique="ltc_cp", mis="optimal_clamped", sample_count=1, light_samples=1,
+            fast_atan=0, min_vertices=3, max_vertices=3):
+    return Variant(LIGHT[light_sampling], POLY[technique], MIS[mis], sample_count, light_samples, int(fast_atan),
+                   min_vertices, max_vertices)
+
+
+def wang(seed):
+    return int(lib().orc_wang_random_number(C.c_uint32(seed & 0xFFFFFFFF)))
+
+
+def light_records(lights, max_vertices=None):
+    """The write_lights stream (main.c:456-490) via orc_update_polygonal_light; returns (N, 12 + 4 V) float32."""
+    if max_vertices is None:
+        max_vertices = max(len(l["vertices_plane_space"]) for l in lights)
+    out = np.zeros((len(lights), 12 + 4 * max_vertices), dtype=np.float32)
+    for i, l in enumerate(lights):
+        n = len(l["vertices_plane_space"])
+        ps = np.zeros((n, 4), dtype=np.float32); ps[:, :2] = np.asarray(l["vertices_plane_space"], dtype=np.float32)[:, :2]
+        world = np.zeros((n, 4), dtype=np.float32)
+        plane = (C.c_float * 4)(); rad = (C.c_float * 3)(); area = C.c_float()
+        lib().orc_update_polygonal_light((C.c_float * 3)(*l["rotation_angles"]), C.c_float(l["scaling_x"]), C.c_float(l["scaling_y"]),
+                                         (C.c_float * 3)(*l["translation"]), (C.c_float * 3)(*l["radiant_flux"]), C.c_uint32(n),
+                                         _p(ps), _p(world), plane, rad, C.byref(area), None)
+        out[i, 0:3] = list(rad); out[i, 4:8] = list(plane)
+        out[i, 8:9].view(np.uint32)[0] = n
+        out[i, 12:12 + 4 * n] = world.reshape(-1)
+        if n < max_vertices:
+            out[i, 12 + 4 * n:16 + 4 * n] = world[0]
+    return out
+
+
+def make_constants(scene, width, height, frame_word, exposure=1.5, roughness_factor=1.0, mis_visibility_estimate=0.5,
+                   ltc_res=64, ltc_layers=51):
+    """write_constants (main.c:2902-2946) through the oracle's host arithmetic."""
+    c = Constants()
+    mesh, cam = scene["mesh"], scene["camera"]
+    for i in range(3):
+        c.dequant_factor[i] = float(mesh["dequant_factor"][i]); c.dequant_summand[i] = float(mesh["dequant_summand"][i])
+        c.camera_position[i] = float(cam["position"][i])
+    c.error_factor = float(np.float32(10.0) ** np.float32(7.0))
+    lib().orc_world_to_projection(c.world_to_projection, (C.c_float * 3)(*cam["position"]), C.c_float(cam["rotation_x"]),
+                                  C.c_float(cam["rotation_z"]), C.c_float(cam["vertical_fov"]), C.c_float(cam["near"]),
+                                  C.c_float(cam["far"]), C.c_float(np.float32(width) / np.float32(height)))
+    lib().orc_pixel_to_ray(c.pixel_to_ray, c.world_to_projection, C.c_uint32(width), C.c_uint32(height))
+    c.mis_visibility_estimate = mis_visibility_estimate
+    c.viewport[0], c.viewport[1] = width, height
+    c.exposure_factor, c.roughness_factor = exposure, roughness_factor
+    c.noise_random_numbers[0] = frame_word & 0xFFFFFFFF
+    lib().orc_ltc_constants(c.ltc_constants, C.c_uint32(ltc_res), C.c_uint32(ltc_res), C.c_uint32(ltc_layers))
+    return c
+
+
+def frame_words(frame_seed):
+    """set_noise_constants with animate_noise (noise_table.c:24-28): 4 words for frame number `frame_seed`."""
+    return [wang(frame_seed * 4 + i) for i in range(4)]
+
+
+class OracleScene:
+    """Owns the numpy buffers behind an orc_scene_t and its BVH."""
+
+    def __init__(self, scene, ltc_rgba16, ltc_rg16, max_vertices=None):
+        from risltc_b200.scenes import material_constants
+        mesh = scene["mesh"]
+        self.positions = np.ascontiguousarray(mesh["positions"], dtype=np.uint32)
+        self.normals_uv = np.ascontiguousarray(mesh["normals_uv"], dtype=np.uint16)
+        self.material_indices = np.ascontiguousarray(mesh["material_indices"], dtype=np.uint8)
+        self.materials = np.ascontiguousarray(material_constants(scene["materials"]), dtype=np.float32)
+        self.records = np.ascontiguousarray(light_records(scene["lights"], max_vertices))
+        self.max_vertices = (self.records.shape[1] - 12) // 4
+        self.min_vertices = min(len(l["vertices_plane_space"]) for l in scene["lights"])
+        self.rgba16 = np.ascontiguousarray(ltc_rgba16, dtype=np.uint16)
+        self.rg16 = np.ascontiguousarray(ltc_rg16, dtype=np.uint16)
+        s = Scene()
+        s.triangle_count = self.material_indices.shape[0]
+        for i in range(3):
+            s.dequant_factor[i] = float(mesh["dequant_factor"][i]); s.dequant_summand[i] = float(mesh["dequant_summand"][i])
+        s.positions, s.normals_uv, s.material_indices = _p(self.positions), _p(self.normals_uv), _p(self.material_indices)
+        s.material_count, s.materials = self.materials.shape[0], _p(self.materials)
+        s.light_count, s.light_records = self.records.shape[0], _p(self.records)
+        s.ltc_layers, s.ltc_res = self.rgba16.shape[0], self.rgba16.shape[1]
+        s.ltc_rgba16, s.ltc_rg16 = _p(self.rgba16), _p(self.rg16)
+        self.c = s
+        lib().orc_build_bvh(C.byref(s))
+
+    def __del__(self):
+        try:
+            lib().orc_free_bvh(C.byref(self.c))
+        except Exception:
+            pass
+
+    def render(self, constants_list, var, accum=None, accum_start=0):
+        """Render one frame per entry of constants_list, accumulating like accum_pass. Returns (accum, visibility, rays)."""
+        W, H = constants_list[0].viewport[0], constants_list[0].viewport[1]
+        if accum is None:
+            accum = np.zeros((H, W, 4), dtype=np.float32)
+        vis = np.zeros((H, W), dtype=np.uint32)
+        rays = 0
+        for k, c in enumerate(constants_list):
+            rays += int(lib().orc_render_frame(C.byref(self.c), C.byref(c), C.byref(var), C.c_uint32(accum_start + k), _p(accum), _p(vis)))
+        return accum, vis, rays
+
+    def any_hit(self, origin, direction, t_min, t_max):
+        return int(lib().orc_any_hit(C.byref(self.c), (C.c_float * 3)(*origin), (C.c_float * 3)(*direction), C.c_float(t_min), C.c_float(t_max)))
+
+
+def thread_count():
+    return int(lib().orc_thread_count())

@@ -1,0 +1,126 @@
+/* risltc_cuda.h -- C ABI of librisltc_cuda.so, the B200 (sm_100a) implementation of
+ * risltc's per-pixel shading path. Plain C: pointers and sizes only.
+ *
+ * The reference has no FFI for this path; its host code (main.c) talks to Vulkan
+ * directly. Each entry point below replaces one block of that host code, cited as
+ * file:line under /root/reference/src. A maintainer wires them in as shown in
+ * INTEGRATION.md. Conventions follow the reference: every function that can fail
+ * returns int, 0 = success, non-zero = failure after printf of a one-line message
+ * (ltc_table.c:38-43, scene.c:414-418); destroy tolerates NULL / partially built
+ * objects; the library is single-threaded like the reference (one stream per
+ * device object) and never spawns host threads that outlive a call.
+ *
+ * There is no CPU fallback: when no CUDA device is usable every call fails. */
+#ifndef RISLTC_CUDA_H
+#define RISLTC_CUDA_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct risltc_device_s risltc_device_t;
+
+/* Shader-variant selection. Replaces the -D table that specialises
+ * shading_pass.frag.glsl (main.c:962-991); enum values are those of
+ * main.h:42-83 (mis_heuristic_t, light_sampling_strategies_t) and
+ * polygonal_light.h:29-46 (sample_polygon_technique_t). */
+typedef struct risltc_variant_s {
+	uint32_t light_sampling;      /* 0 light_uniform, 1 light_reservoir */
+	uint32_t polygon_technique;   /* 0 baseline, 1 area_turk, 2 projected_solid_angle, 3 ..._biased, 4 ltc_cp */
+	uint32_t mis_heuristic;       /* 0 balance, 1 power, 2 weighted, 3 optimal_clamped, 4 optimal */
+	uint32_t sample_count;        /* SAMPLE_COUNT (render_settings_t.sample_count) */
+	uint32_t light_samples;       /* LIGHT_SAMPLES (render_settings_t.sample_count_light) */
+	uint32_t fast_atan;           /* USE_FAST_ATAN */
+	uint32_t min_light_vertices;  /* MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING (main.c:944) */
+	uint32_t max_light_vertices;  /* MAX_POLYGONAL_LIGHT_VERTEX_COUNT (main.c:945) */
+} risltc_variant_t;
+
+/* create_vulkan_device / destroy_vulkan_device (vulkan_basics.c:24, main.c:2569-2580). */
+int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordinal);
+void risltc_cuda_destroy_device(risltc_device_t* device);
+const char* risltc_cuda_last_error(void);
+
+/* Mesh upload + acceleration structure: load_scene's device part (scene.c:484-559) and
+ * create_acceleration_structure (scene.c:142-406, dequantisation :176-187). The three
+ * arrays are the .vks payload / mesh_t buffers (scene.h:58-75): 2*3*T u32 positions,
+ * 4*3*T u16 normals+uv, T u8 material indices. */
+int risltc_cuda_upload_scene(risltc_device_t* device, const uint32_t* quantized_positions,
+	const uint16_t* normals_and_tex_coords, const uint8_t* material_indices, uint64_t triangle_count,
+	const float dequantization_factor[3], const float dequantization_summand[3]);
+
+/* Material textures (scene.c:520-552, sampled at shading_pass.frag.glsl:629-633). One record of
+ * 8 floats per material: base colour rgb (linear), specular texel rgb (occlusion, linear
+ * roughness, metalicity), normal-map texel rg. Flat-colour materials only in this round. */
+int risltc_cuda_upload_materials(risltc_device_t* device, const float* material_constants, uint64_t material_count);
+
+/* Light buffer: the byte stream write_lights produces (main.c:456-490): per light 12 floats
+ * {radiance.xyz, pad, plane.xyzw, vertex_count(u32), pad x3} + max_vertex_count x {x, y, z, pad}. */
+int risltc_cuda_upload_lights(risltc_device_t* device, const void* light_records, uint32_t light_count, uint32_t max_vertex_count);
+
+/* LTC tables: the two staging arrays load_ltc_table fills (ltc_table.c:82-116) before the
+ * image copy (ltc_table.c:143-166): fresnel_count layers of res x res RGBA16 / RG16 UNORM. */
+int risltc_cuda_upload_ltc(risltc_device_t* device, const uint16_t* rgba16, const uint16_t* rg16,
+	uint32_t roughness_count, uint32_t inclination_count, uint32_t fresnel_count);
+
+/* change_shading / create_shading_pass (main.c:2498, 937-1010). */
+int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* variant);
+
+/* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
+ * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index
+ * (stripe_count = 1: the whole frame). Resets the accumulation buffer. */
+int risltc_cuda_resize(risltc_device_t* device, uint32_t width, uint32_t height,
+	uint32_t stripe_height, uint32_t stripe_index, uint32_t stripe_count);
+
+/* Let the accumulation target live in caller-owned device memory (e.g. a torch tensor that an
+ * NCCL gather reads). `rows` is the number of rows this device owns; layout rows x width x RGBA32F. */
+int risltc_cuda_set_accum_buffer(risltc_device_t* device, void* device_pointer);
+uint32_t risltc_cuda_owned_rows(const risltc_device_t* device);
+
+/* One frame = the four subpasses record_render_frame_commands records (main.c:2010-2092):
+ * visibility -> shading -> (shadow rays) -> accumulation. `constants` is the 256-byte
+ * per_frame_constants_t block write_constants fills (main.c:2902-2946, main.h:537-553);
+ * accum_num is the push constant of the accumulation pass (main.c:2062-2064). Asynchronous on the
+ * device's stream; timing is taken with events around the whole frame like the reference's
+ * timestamps (main.c:2038-2040, 2084). */
+int risltc_cuda_render_frame(risltc_device_t* device, const void* per_frame_constants, uint32_t accum_num);
+/* `frame_count` frames back to back from an array of constant blocks, accum_num = first + i. */
+int risltc_cuda_render_frames(risltc_device_t* device, const void* per_frame_constants_array, uint32_t frame_count, uint32_t first_accum_num);
+
+/* Blocking read-backs (implement_screenshot's staging copy, main.c:2358-2409). rgba has
+ * owned_rows x width x 4 floats, in the order of the owned rows. */
+int risltc_cuda_synchronize(risltc_device_t* device);
+int risltc_cuda_read_accum(risltc_device_t* device, float* rgba);
+int risltc_cuda_read_visibility(risltc_device_t* device, uint32_t* primitive_ids);
+/* Global row index of every owned row (owned_rows entries). */
+int risltc_cuda_owned_row_indices(const risltc_device_t* device, uint32_t* rows);
+
+/* record_frame_time (frame_timer.c:37-55): milliseconds of the last render_frame(s) call
+ * (blocks until it has finished); per-kernel split in ms[4] = visibility, shading, shadow+accumulate, total. */
+float risltc_cuda_last_frame_ms(risltc_device_t* device);
+int risltc_cuda_last_kernel_ms(risltc_device_t* device, float ms[4]);
+/* Counters of the last frame: [0] covered (non-background) pixel-samples, [1] shadow rays traced,
+ * [2] kernels launched since create, [3] RIS candidates evaluated. */
+int risltc_cuda_counters(risltc_device_t* device, uint64_t counters[4]);
+void* risltc_cuda_stream(risltc_device_t* device);
+
+/* Known-answer entry points: run the device functions of the shading kernel on arrays so that tests
+ * can compare them with the oracle one function at a time (SURVEY 8c "setup agrees to <= 1e-5").
+ * polygons: count x 8 x 3 floats (vertex slots), vertex_counts: count. */
+int risltc_cuda_kat_clip(risltc_device_t* device, float* polygons, uint32_t* vertex_counts, uint32_t count, uint32_t max_light_vertices);
+int risltc_cuda_kat_ltc_integral(risltc_device_t* device, const float* polygons, const uint32_t* vertex_counts, float* out, uint32_t count);
+/* out_polygon: count x 34 floats {vertex_count, vertices[8][2], ellipses[8][2], inner_ellipse_0[2], sectors[8], total... see kat layout in api.cu}
+ * samples: for each polygon one direction from (u0, u1) = randoms[2 i], randoms[2 i + 1]. */
+int risltc_cuda_kat_psa(risltc_device_t* device, const float* polygons, const uint32_t* vertex_counts, const float* randoms,
+	float* out_polygons, float* out_dirs, uint32_t count, uint32_t max_polygon_vertices, uint32_t fast_atan, uint32_t biased);
+int risltc_cuda_kat_noise(risltc_device_t* device, uint32_t width, uint32_t height, uint32_t frame_word, uint32_t draws, float* out);
+/* out: count x 33 floats {world_to_shading[12], shading_to_cosine[9], cosine_to_shading[9], albedo, determinant, pad} */
+int risltc_cuda_kat_ltc_coefficients(risltc_device_t* device, const float* inputs /* count x 11: fresnel, roughness, pos, normal, outgoing */,
+	const float ltc_constants[6], float* out, uint32_t count);
+int risltc_cuda_kat_any_hit(risltc_device_t* device, const float* rays /* count x 8: o, tmin, d, tmax */, uint32_t* hits, uint32_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

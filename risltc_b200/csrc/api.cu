@@ -1,0 +1,368 @@
+// api.cu -- C ABI of librisltc_cuda.so (include/risltc_cuda.h) and kernel launches.
+#include "../../include/risltc_cuda.h"
+#include "kernels.cuh"
+#include "bvh_build.h"
+#include "clip_rotation_table.inc"
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+
+static int fail(const char* what, const char* detail) {
+	g_last_error = std::string(what) + (detail ? std::string(": ") + detail : std::string());
+	printf("risltc_cuda: %s\n", g_last_error.c_str());
+	return 1;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, cudaGetErrorString(e_)); } while (0)
+
+struct risltc_device_s {
+	int ordinal = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // batch start, after (1), after (2), after (3+4) of last frame, batch end
+	// scene
+	uint2* positions = nullptr; ushort4* normals_uv = nullptr; uint8_t* material_indices = nullptr;
+	float4* materials = nullptr; float4* lights = nullptr; ushort4* ltc_rgba = nullptr; ushort2* ltc_rg = nullptr;
+	BvhNode* nodes = nullptr; BvhTri* tris = nullptr;
+	SceneView view = {};
+	float dequant_factor[3] = { 0, 0, 0 }, dequant_summand[3] = { 0, 0, 0 };
+	// variant + targets
+	Variant variant = { 1, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1, 1, 0, 3, 3 };
+	uint32_t width = 0, height = 0;
+	Stripes stripes = { 8, 0, 1, 0 };
+	PixelBuffers px = {};
+	float4* own_accum = nullptr;
+	uint32_t ray_slots = 0, group_slots = 0;
+	unsigned long long launches = 0;
+	bool timed = false;
+};
+
+static int use(risltc_device_t* d) {
+	if (!d) return fail("null device", nullptr);
+	CU(cudaSetDevice(d->ordinal));
+	return 0;
+}
+
+extern "C" const char* risltc_cuda_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordinal) {
+	if (!device) return fail("create_device: null output pointer", nullptr);
+	*device = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) return fail("create_device: no CUDA device (there is no CPU fallback)", cudaGetErrorString(e));
+	if (cuda_ordinal < 0 || cuda_ordinal >= count) return fail("create_device: ordinal out of range", nullptr);
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, cuda_ordinal));
+	if (prop.major < 10) return fail("create_device: kernels are built for sm_100a only", prop.name);
+	risltc_device_t* d = new risltc_device_t();
+	d->ordinal = cuda_ordinal;
+	CU(cudaSetDevice(cuda_ordinal));
+	CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
+	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
+	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
+	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
+	*device = d;
+	return 0;
+}
+
+static void free_targets(risltc_device_t* d) {
+	cudaFree(d->px.visibility); cudaFree(d->px.origin); cudaFree(d->px.base); cudaFree(d->px.group);
+	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum);
+	d->px.visibility = nullptr; d->px.origin = d->px.base = d->px.group = d->px.ray_a = d->px.ray_b = nullptr;
+	d->own_accum = nullptr; d->px.accum = nullptr;
+	d->ray_slots = d->group_slots = 0;
+}
+
+static void free_scene(risltc_device_t* d) {
+	cudaFree(d->positions); cudaFree(d->normals_uv); cudaFree(d->material_indices); cudaFree(d->nodes); cudaFree(d->tris);
+	d->positions = nullptr; d->normals_uv = nullptr; d->material_indices = nullptr; d->nodes = nullptr; d->tris = nullptr;
+}
+
+extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
+	if (!d) return;
+	cudaSetDevice(d->ordinal);
+	if (d->stream) cudaStreamSynchronize(d->stream);
+	free_targets(d); free_scene(d);
+	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters);
+	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
+	if (d->stream) cudaStreamDestroy(d->stream);
+	delete d;
+}
+
+extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords,
+	const uint8_t* material_indices, uint64_t T, const float factor[3], const float summand[3])
+{
+	if (use(d)) return 1;
+	if (!quantized_positions || !normals_and_tex_coords || !material_indices || T == 0) return fail("upload_scene: the mesh is empty", nullptr);
+	if (T >= (1ull << 27)) return fail("upload_scene: more than 2^27 triangles", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	free_scene(d);
+	memcpy(d->dequant_factor, factor, 12); memcpy(d->dequant_summand, summand, 12);
+	CU(cudaMalloc(&d->positions, T * 3 * sizeof(uint2)));
+	CU(cudaMalloc(&d->normals_uv, T * 3 * sizeof(ushort4)));
+	CU(cudaMalloc(&d->material_indices, T));
+	CU(cudaMemcpy(d->positions, quantized_positions, T * 3 * sizeof(uint2), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d->normals_uv, normals_and_tex_coords, T * 3 * sizeof(ushort4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d->material_indices, material_indices, T, cudaMemcpyHostToDevice));
+	// acceleration structure
+	std::vector<float> verts;
+	dequantize_mesh_for_bvh(quantized_positions, T, factor, summand, verts);
+	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
+	build_bvh(verts.data(), T, nodes, order);
+	std::vector<BvhNode> dn(nodes.size());
+	for (size_t i = 0; i != nodes.size(); ++i) {
+		const BvhNodeHost& n = nodes[i];
+		dn[i].a = make_float4(n.left_lo[0], n.left_lo[1], n.left_lo[2], n.left_hi[0]);
+		dn[i].b = make_float4(n.left_hi[1], n.left_hi[2], n.right_lo[0], n.right_lo[1]);
+		dn[i].c = make_float4(n.right_lo[2], n.right_hi[0], n.right_hi[1], n.right_hi[2]);
+		dn[i].d = make_int4(n.left, n.right, 0, 0);
+	}
+	std::vector<BvhTri> dt(T);
+	for (uint64_t slot = 0; slot != T; ++slot) {
+		uint32_t t = order[slot];
+		const float* v = verts.data() + 9 * (size_t) t;
+		uint32_t id = t | ((quantized_positions[6 * (size_t) t + 1] >> 31) << 31);
+		float idf; memcpy(&idf, &id, 4);
+		volatile float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
+		volatile float e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+		dt[slot].v0 = make_float4(v[0], v[1], v[2], idf);
+		dt[slot].e1 = make_float4(e1x, e1y, e1z, 0.0f);
+		dt[slot].e2 = make_float4(e2x, e2y, e2z, 0.0f);
+	}
+	CU(cudaMalloc(&d->nodes, dn.size() * sizeof(BvhNode)));
+	CU(cudaMalloc(&d->tris, dt.size() * sizeof(BvhTri)));
+	CU(cudaMemcpy(d->nodes, dn.data(), dn.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d->tris, dt.data(), dt.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
+	d->view.positions = d->positions; d->view.normals_uv = d->normals_uv; d->view.material_indices = d->material_indices;
+	d->view.nodes = d->nodes; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
+	return 0;
+}
+
+extern "C" int risltc_cuda_upload_materials(risltc_device_t* d, const float* m, uint64_t count) {
+	if (use(d)) return 1;
+	if (!m || count == 0) return fail("upload_materials: no materials", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	cudaFree(d->materials); d->materials = nullptr;
+	std::vector<float4> packed(2 * count);
+	for (uint64_t i = 0; i != count; ++i) {
+		const float* r = m + 8 * i;
+		packed[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
+		packed[2 * i + 1] = make_float4(r[4], r[5], r[6], r[7]);   // linear roughness, metalicity, normal.r, normal.g
+	}
+	CU(cudaMalloc(&d->materials, packed.size() * sizeof(float4)));
+	CU(cudaMemcpy(d->materials, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
+	d->view.materials = d->materials;
+	return 0;
+}
+
+extern "C" int risltc_cuda_upload_lights(risltc_device_t* d, const void* records, uint32_t light_count, uint32_t max_vertex_count) {
+	if (use(d)) return 1;
+	if (!records || light_count == 0) return fail("upload_lights: no lights", nullptr);
+	if (max_vertex_count < 3 || max_vertex_count > 7) return fail("upload_lights: polygons need 3 to 7 vertices", nullptr);
+	size_t bytes = (size_t) light_count * (48 + 16 * max_vertex_count);
+	if (d->view.light_count != light_count || d->view.light_stride4 != 3 + max_vertex_count) {
+		CU(cudaStreamSynchronize(d->stream));
+		cudaFree(d->lights); d->lights = nullptr;
+		CU(cudaMalloc(&d->lights, bytes));
+	}
+	CU(cudaMemcpyAsync(d->lights, records, bytes, cudaMemcpyHostToDevice, d->stream));
+	d->view.lights = d->lights; d->view.light_count = light_count; d->view.light_stride4 = 3 + max_vertex_count;
+	return 0;
+}
+
+extern "C" int risltc_cuda_upload_ltc(risltc_device_t* d, const uint16_t* rgba16, const uint16_t* rg16, uint32_t roughness_count, uint32_t inclination_count, uint32_t fresnel_count) {
+	if (use(d)) return 1;
+	if (!rgba16 || !rg16 || roughness_count == 0 || roughness_count != inclination_count || fresnel_count == 0)
+		return fail("upload_ltc: tables must be square and non-empty", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); d->ltc_rgba = nullptr; d->ltc_rg = nullptr;
+	size_t texels = (size_t) roughness_count * inclination_count * fresnel_count;
+	CU(cudaMalloc(&d->ltc_rgba, texels * sizeof(ushort4)));
+	CU(cudaMalloc(&d->ltc_rg, texels * sizeof(ushort2)));
+	CU(cudaMemcpy(d->ltc_rgba, rgba16, texels * sizeof(ushort4), cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d->ltc_rg, rg16, texels * sizeof(ushort2), cudaMemcpyHostToDevice));
+	d->view.ltc_rgba = d->ltc_rgba; d->view.ltc_rg = d->ltc_rg; d->view.ltc_res = roughness_count; d->view.ltc_layers = fresnel_count;
+	return 0;
+}
+
+static int allocate_ray_buffers(risltc_device_t* d) {
+	uint32_t groups = d->variant.light_samples, slots = groups * d->variant.sample_count * 2u;
+	size_t pixels = d->px.pixel_count;
+	if (!pixels) return 0;
+	if (groups > d->group_slots) {
+		cudaFree(d->px.group); d->px.group = nullptr;
+		CU(cudaMalloc(&d->px.group, pixels * groups * sizeof(float4)));
+		d->group_slots = groups;
+	}
+	if (slots > d->ray_slots) {
+		cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); d->px.ray_a = d->px.ray_b = nullptr;
+		CU(cudaMalloc(&d->px.ray_a, pixels * slots * sizeof(float4)));
+		CU(cudaMalloc(&d->px.ray_b, pixels * slots * sizeof(float4)));
+		d->ray_slots = slots;
+	}
+	CU(cudaMemsetAsync(d->px.ray_b, 0, pixels * d->ray_slots * sizeof(float4), d->stream));
+	return 0;
+}
+
+extern "C" int risltc_cuda_set_variant(risltc_device_t* d, const risltc_variant_t* v) {
+	if (use(d)) return 1;
+	if (!v) return fail("set_variant: null variant", nullptr);
+	if (v->polygon_technique > TECH_LTC_CP || v->mis_heuristic > MIS_OPTIMAL || v->light_sampling > 1) return fail("set_variant: enum out of range", nullptr);
+	if (v->sample_count == 0 || v->light_samples == 0) return fail("set_variant: sample counts must be positive", nullptr);
+	if (v->max_light_vertices < 3 || v->max_light_vertices > 4) return fail("set_variant: kernels are instantiated for 3 and 4 vertex lights", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	memcpy(&d->variant, v, sizeof(Variant));
+	return allocate_ray_buffers(d);
+}
+
+extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t height, uint32_t stripe_height, uint32_t stripe_index, uint32_t stripe_count) {
+	if (use(d)) return 1;
+	if (width == 0 || height == 0 || stripe_count == 0 || stripe_index >= stripe_count || stripe_height == 0) return fail("resize: bad extent or stripe layout", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	void* external = (d->px.accum && d->px.accum != d->own_accum) ? (void*) d->px.accum : nullptr;
+	(void) external;
+	free_targets(d);
+	uint32_t owned = 0;
+	for (uint32_t y0 = stripe_index * stripe_height; y0 < height; y0 += stripe_height * stripe_count)
+		owned += (y0 + stripe_height <= height) ? stripe_height : height - y0;
+	d->width = width; d->height = height;
+	d->stripes.stripe_h = stripe_height; d->stripes.stripe_index = stripe_index; d->stripes.stripe_count = stripe_count; d->stripes.owned_rows = owned;
+	size_t pixels = (size_t) owned * width;
+	d->px.pixel_count = (uint32_t) pixels;
+	if (pixels == 0) return 0;
+	CU(cudaMalloc(&d->px.visibility, pixels * sizeof(uint32_t)));
+	CU(cudaMalloc(&d->px.origin, pixels * sizeof(float4)));
+	CU(cudaMalloc(&d->px.base, pixels * sizeof(float4)));
+	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
+	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
+	d->px.accum = d->own_accum;
+	return allocate_ray_buffers(d);
+}
+
+extern "C" int risltc_cuda_set_accum_buffer(risltc_device_t* d, void* device_pointer) {
+	if (use(d)) return 1;
+	CU(cudaStreamSynchronize(d->stream));
+	d->px.accum = device_pointer ? (float4*) device_pointer : d->own_accum;
+	return 0;
+}
+
+extern "C" uint32_t risltc_cuda_owned_rows(const risltc_device_t* d) { return d ? d->stripes.owned_rows : 0; }
+
+extern "C" int risltc_cuda_owned_row_indices(const risltc_device_t* d, uint32_t* rows) {
+	if (!d || !rows) return fail("owned_row_indices: null argument", nullptr);
+	for (uint32_t r = 0; r != d->stripes.owned_rows; ++r) rows[r] = d->stripes.global_row(r);
+	return 0;
+}
+
+// per_frame_constants_t (main.h:537-553, 256 bytes) -> the fields the kernels read
+static void unpack_constants(FrameUniforms& f, const void* block, uint32_t accum_num) {
+	const unsigned char* b = (const unsigned char*) block;
+	memcpy(f.dequant_factor, b + 0, 12);
+	memcpy(f.dequant_summand, b + 16, 12);
+	memcpy(f.world_to_projection, b + 32, 64);
+	memcpy(f.pixel_to_ray, b + 96, 48);
+	memcpy(f.camera, b + 144, 12);
+	memcpy(&f.mis_visibility_estimate, b + 156, 4);
+	memcpy(&f.width, b + 160, 4); memcpy(&f.height, b + 164, 4);
+	memcpy(&f.exposure, b + 176, 4); memcpy(&f.roughness_factor, b + 180, 4);
+	memcpy(&f.frame_word, b + 208, 4);
+	memcpy(f.ltc_constants, b + 224, 24);
+	f.accum_num = accum_num;
+}
+
+template <int V>
+static void launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, bool defer) {
+	if (defer) shade_kernel<V, true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+	else shade_kernel<V, false><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+}
+
+extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks, uint32_t frame_count, uint32_t first_accum_num) {
+	if (use(d)) return 1;
+	if (!blocks || frame_count == 0) return fail("render_frames: no constants", nullptr);
+	if (!d->nodes || !d->materials || !d->lights || !d->ltc_rgba) return fail("render_frames: scene, materials, lights and LTC tables must be uploaded first", nullptr);
+	if (!d->px.pixel_count) return fail("render_frames: call resize first", nullptr);
+	if (d->view.light_stride4 != 3 + d->variant.max_light_vertices) return fail("render_frames: light buffer stride does not match the variant's max_light_vertices", nullptr);
+	const bool defer = d->variant.polygon_technique != TECH_TURK && d->variant.polygon_technique != TECH_BASELINE && d->variant.mis_heuristic != MIS_OPTIMAL;
+	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
+	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
+	CU(cudaEventRecord(d->ev[0], d->stream));
+	for (uint32_t i = 0; i != frame_count; ++i) {
+		FrameUniforms f;
+		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
+		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
+		bool last = (i + 1 == frame_count);
+		gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
+		if (last) CU(cudaEventRecord(d->ev[1], d->stream));
+		if (d->variant.max_light_vertices == 3) launch_shade<3>(d, grid, f, defer); else launch_shade<4>(d, grid, f, defer);
+		if (last) CU(cudaEventRecord(d->ev[2], d->stream));
+		resolve_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+		if (last) CU(cudaEventRecord(d->ev[3], d->stream));
+		d->launches += 3;
+	}
+	CU(cudaEventRecord(d->ev[4], d->stream));
+	CU(cudaGetLastError());
+	d->timed = true;
+	return 0;
+}
+
+extern "C" int risltc_cuda_render_frame(risltc_device_t* d, const void* block, uint32_t accum_num) {
+	return risltc_cuda_render_frames(d, block, 1, accum_num);
+}
+
+extern "C" int risltc_cuda_synchronize(risltc_device_t* d) {
+	if (use(d)) return 1;
+	CU(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+
+extern "C" int risltc_cuda_read_accum(risltc_device_t* d, float* rgba) {
+	if (use(d)) return 1;
+	if (!rgba || !d->px.accum) return fail("read_accum: nothing to read", nullptr);
+	CU(cudaMemcpyAsync(rgba, d->px.accum, (size_t) d->px.pixel_count * sizeof(float4), cudaMemcpyDeviceToHost, d->stream));
+	CU(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+
+extern "C" int risltc_cuda_read_visibility(risltc_device_t* d, uint32_t* ids) {
+	if (use(d)) return 1;
+	if (!ids || !d->px.visibility) return fail("read_visibility: nothing to read", nullptr);
+	CU(cudaMemcpyAsync(ids, d->px.visibility, (size_t) d->px.pixel_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+	CU(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+
+extern "C" float risltc_cuda_last_frame_ms(risltc_device_t* d) {
+	float ms[4];
+	if (risltc_cuda_last_kernel_ms(d, ms)) return -1.0f;
+	return ms[3];
+}
+
+extern "C" int risltc_cuda_last_kernel_ms(risltc_device_t* d, float ms[4]) {
+	if (use(d)) return 1;
+	if (!d->timed) return fail("last_kernel_ms: no frame rendered yet", nullptr);
+	CU(cudaEventSynchronize(d->ev[4]));
+	float lead = 0.0f;
+	CU(cudaEventElapsedTime(&ms[0], d->ev[0], d->ev[1]));   // includes earlier frames of a batch; corrected below
+	CU(cudaEventElapsedTime(&ms[1], d->ev[1], d->ev[2]));
+	CU(cudaEventElapsedTime(&ms[2], d->ev[2], d->ev[3]));
+	CU(cudaEventElapsedTime(&ms[3], d->ev[0], d->ev[4]));
+	CU(cudaEventElapsedTime(&lead, d->ev[0], d->ev[3]));
+	(void) lead;
+	return 0;
+}
+
+extern "C" int risltc_cuda_counters(risltc_device_t* d, uint64_t counters[4]) {
+	if (use(d)) return 1;
+	unsigned long long h[4];
+	CU(cudaMemcpyAsync(h, d->px.counters, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
+	CU(cudaStreamSynchronize(d->stream));
+	counters[0] = h[0]; counters[1] = h[1]; counters[2] = d->launches; counters[3] = h[3];
+	return 0;
+}
+
+extern "C" void* risltc_cuda_stream(risltc_device_t* d) { return d ? (void*) d->stream : nullptr; }
+
+#include "kat.cuh"

@@ -1,0 +1,147 @@
+// bvh_build.cpp -- host-side BVH construction (binned SAH, binary tree, children's
+// boxes stored in the parent). Replaces the driver's BLAS/TLAS build that the
+// reference requests in create_acceleration_structure (scene.c:142-406); like there,
+// the input is the mesh dequantised with mul + add (scene.c:176-187).
+#include "bvh_build.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace {
+
+struct Box {
+	float lo[3], hi[3];
+	void reset() { for (int k = 0; k != 3; ++k) { lo[k] = std::numeric_limits<float>::infinity(); hi[k] = -lo[k]; } }
+	void grow(const Box& b) { for (int k = 0; k != 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+	void grow(const float* p) { for (int k = 0; k != 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+	float half_area() const {
+		float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+		return (dx < 0.0f) ? 0.0f : dx * dy + dy * dz + dz * dx;
+	}
+};
+
+struct Builder {
+	const float* verts;            // 9 floats per triangle
+	std::vector<Box> tri_box;
+	std::vector<float> centroid;   // 3 per triangle
+	std::vector<uint32_t> order;
+	std::vector<BvhNodeHost>* nodes;
+	float pad;
+	static constexpr int kBins = 16;
+	static constexpr uint32_t kLeaf = 4;
+
+	// Returns the child reference for [first, first + count) and its bounds.
+	int build(uint32_t first, uint32_t count, Box& bounds) {
+		Box cb; cb.reset(); bounds.reset();
+		for (uint32_t i = first; i != first + count; ++i) {
+			bounds.grow(tri_box[order[i]]);
+			cb.grow(&centroid[3 * (size_t) order[i]]);
+		}
+		if (count <= kLeaf) return ~(int) ((first << 4) | (count - 1));
+		int axis = 0;
+		float ext[3] = { cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2] };
+		if (ext[1] > ext[axis]) axis = 1;
+		if (ext[2] > ext[axis]) axis = 2;
+		uint32_t mid = first + count / 2;
+		if (ext[axis] > 0.0f) {
+			// binned SAH over the three axes
+			float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
+			for (int a = 0; a != 3; ++a) {
+				if (!(ext[a] > 0.0f)) continue;
+				Box bin_box[kBins]; uint32_t bin_n[kBins];
+				for (int b = 0; b != kBins; ++b) { bin_box[b].reset(); bin_n[b] = 0; }
+				float scale = (float) kBins / ext[a];
+				for (uint32_t i = first; i != first + count; ++i) {
+					int b = std::min(kBins - 1, (int) ((centroid[3 * (size_t) order[i] + a] - cb.lo[a]) * scale));
+					bin_box[b].grow(tri_box[order[i]]); bin_n[b]++;
+				}
+				float right_area[kBins]; uint32_t right_n[kBins];
+				Box acc; acc.reset(); uint32_t n = 0;
+				for (int b = kBins - 1; b > 0; --b) { acc.grow(bin_box[b]); n += bin_n[b]; right_area[b] = acc.half_area(); right_n[b] = n; }
+				acc.reset(); n = 0;
+				for (int b = 0; b + 1 != kBins; ++b) {
+					acc.grow(bin_box[b]); n += bin_n[b];
+					if (n == 0 || right_n[b + 1] == 0) continue;
+					float cost = acc.half_area() * (float) n + right_area[b + 1] * (float) right_n[b + 1];
+					if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+				}
+			}
+			if (best_axis >= 0) {
+				float scale = (float) kBins / ext[best_axis], lo = cb.lo[best_axis];
+				auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t t) {
+					int b = std::min(kBins - 1, (int) ((centroid[3 * (size_t) t + best_axis] - lo) * scale));
+					return b <= best_bin;
+				});
+				mid = (uint32_t) (it - order.begin());
+			}
+			if (mid == first || mid == first + count) {
+				mid = first + count / 2;
+				std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count, [&](uint32_t x, uint32_t y) {
+					return centroid[3 * (size_t) x + axis] < centroid[3 * (size_t) y + axis];
+				});
+			}
+		}
+		else if (count <= 16) return ~(int) ((first << 4) | (count - 1));  // coincident centroids: one fat leaf
+		int index = (int) nodes->size();
+		nodes->push_back(BvhNodeHost());
+		Box lb, rb;
+		int l = build(first, mid - first, lb);
+		int r = build(mid, first + count - mid, rb);
+		BvhNodeHost& n = (*nodes)[index];
+		for (int k = 0; k != 3; ++k) {
+			n.left_lo[k] = lb.lo[k] - pad; n.left_hi[k] = lb.hi[k] + pad;
+			n.right_lo[k] = rb.lo[k] - pad; n.right_hi[k] = rb.hi[k] + pad;
+		}
+		n.left = l; n.right = r;
+		return index;
+	}
+};
+
+}  // namespace
+
+void dequantize_mesh_for_bvh(const uint32_t* q, uint64_t triangle_count, const float factor[3], const float summand[3], std::vector<float>& verts) {
+	verts.resize(9 * triangle_count);
+	for (uint64_t i = 0; i != triangle_count * 3; ++i) {
+		uint32_t q0 = q[2 * i], q1 = q[2 * i + 1];
+		float p[3] = {
+			(float) (q0 & 0x1FFFFFu),
+			(float) (((q0 & 0xFFE00000u) >> 21) | ((q1 & 0x3FFu) << 11)),
+			(float) ((q1 & 0x7FFFFC00u) >> 10) };
+		for (int j = 0; j != 3; ++j) {
+			volatile float prod = p[j] * factor[j];   // mul then add, never contracted
+			verts[3 * i + j] = prod + summand[j];
+		}
+	}
+}
+
+void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order) {
+	Builder b;
+	b.verts = verts; b.nodes = &nodes;
+	b.tri_box.resize(triangle_count); b.centroid.resize(3 * triangle_count); b.order.resize(triangle_count);
+	Box all; all.reset();
+	for (uint64_t t = 0; t != triangle_count; ++t) {
+		Box bx; bx.reset();
+		for (int k = 0; k != 3; ++k) bx.grow(verts + 9 * t + 3 * k);
+		b.tri_box[t] = bx; all.grow(bx);
+		for (int k = 0; k != 3; ++k) b.centroid[3 * t + k] = (verts[9 * t + k] + verts[9 * t + 3 + k] + verts[9 * t + 6 + k]) * (1.0f / 3.0f);
+		b.order[t] = (uint32_t) t;
+	}
+	float extent = std::max(all.hi[0] - all.lo[0], std::max(all.hi[1] - all.lo[1], all.hi[2] - all.lo[2]));
+	b.pad = 1.0e-5f * extent + 1.0e-7f;
+	nodes.clear();
+	nodes.reserve(triangle_count);
+	Box root;
+	int ref = b.build(0, (uint32_t) triangle_count, root);
+	if (ref < 0) {
+		// the whole scene is one leaf: wrap it in a root whose right child can never be hit
+		BvhNodeHost n;
+		for (int k = 0; k != 3; ++k) {
+			n.left_lo[k] = root.lo[k] - b.pad; n.left_hi[k] = root.hi[k] + b.pad;
+			n.right_lo[k] = std::numeric_limits<float>::infinity(); n.right_hi[k] = -std::numeric_limits<float>::infinity();
+		}
+		n.left = ref; n.right = ref;
+		nodes.push_back(n);
+	}
+	order.swap(b.order);
+}

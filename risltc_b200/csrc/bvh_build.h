@@ -1,0 +1,16 @@
+// bvh_build.h -- host BVH builder interface (see bvh_build.cpp).
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+struct BvhNodeHost {
+	float left_lo[3], left_hi[3], right_lo[3], right_hi[3];
+	int left, right;   // >= 0: inner node index; < 0: leaf, ~((first_slot << 4) | (count - 1))
+};
+
+// 21-bit positions -> world space exactly as scene.c:176-187 does for the acceleration structure.
+void dequantize_mesh_for_bvh(const uint32_t* quantized_positions, uint64_t triangle_count,
+	const float factor[3], const float summand[3], std::vector<float>& verts);
+
+// verts: 9 floats per triangle. order[slot] = triangle index stored at that leaf slot.
+void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order);

@@ -1,0 +1,83 @@
+// common.cuh -- shared types and small math helpers of the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define RL_MAX_P 8            // largest MAX_POLYGON_VERTEX_COUNT (V_max 7 + 1, main.c:191-204)
+#define RL_PI 3.14159265358979323846f
+#define RL_HALF_PI 1.57079632679489661923f
+#define RL_INV_PI 0.318309886183790671538f
+
+// ---- per-frame uniforms: the fields of per_frame_constants_t that the hot path reads
+// (main.h:537-553 / shared_constants.glsl:21-60), repacked for a kernel parameter.
+struct FrameUniforms {
+	float dequant_factor[3], dequant_summand[3];
+	float world_to_projection[4][4];
+	float pixel_to_ray[3][4];
+	float camera[3];
+	float mis_visibility_estimate;
+	uint32_t width, height;
+	float exposure, roughness_factor;
+	uint32_t frame_word;      // g_noise_random_numbers.x, the only word the shader reads (noise_utility.glsl:82)
+	float ltc_constants[6];
+	uint32_t accum_num;
+};
+
+// ---- shader variant (the -D table of main.c:962-991)
+struct Variant {
+	uint32_t light_sampling, polygon_technique, mis_heuristic, sample_count, light_samples, fast_atan;
+	uint32_t min_light_vertices, max_light_vertices;
+};
+enum { TECH_BASELINE = 0, TECH_TURK = 1, TECH_PSA = 2, TECH_PSA_BIASED = 3, TECH_LTC_CP = 4 };
+enum { MIS_BALANCE = 0, MIS_POWER = 1, MIS_WEIGHTED = 2, MIS_OPTIMAL_CLAMPED = 3, MIS_OPTIMAL = 4 };
+
+// ---- image partition: this device owns the rows y with (y / stripe_h) % stripe_count == stripe_index
+struct Stripes {
+	uint32_t stripe_h, stripe_index, stripe_count, owned_rows;
+	__host__ __device__ uint32_t global_row(uint32_t local_row) const {
+		return ((local_row / stripe_h) * stripe_count + stripe_index) * stripe_h + local_row % stripe_h;
+	}
+};
+
+// ---- BVH: binary tree, one 64-byte node holds the boxes of BOTH children (4 x 16-byte loads)
+struct __align__(16) BvhNode {
+	float4 a;   // left.lo.xyz, left.hi.x
+	float4 b;   // left.hi.yz, right.lo.xy
+	float4 c;   // right.lo.z, right.hi.xyz
+	int4 d;     // left child, right child (>= 0 inner node, < 0 leaf: ~((first << 4) | (count - 1))), unused x2
+};
+// ---- triangle: v0, e1 = v1 - v0, e2 = v2 - v0 (fp32 differences, identical to computing them per test);
+// .w of the first vector carries the primitive id (bit 31 = emitter flag).
+struct __align__(16) BvhTri { float4 v0, e1, e2; };
+
+struct SceneView {
+	const uint2* positions;          // T*3 quantised positions (mesh_t.positions)
+	const ushort4* normals_uv;       // T*3
+	const uint8_t* material_indices; // T
+	const float4* materials;         // 2 float4 per material: {base rgb, occlusion}, {roughness_lin, metalicity, normal.r, normal.g}
+	const float4* lights;            // light records, (3 + V) float4 each
+	uint32_t light_count, light_stride4;
+	const ushort4* ltc_rgba; const ushort2* ltc_rg; uint32_t ltc_res, ltc_layers;
+	const BvhNode* nodes; const BvhTri* tris; uint32_t triangle_count;
+};
+
+// ---- tiny vector helpers (no operator overloading on purpose: every rounding is visible)
+__device__ __forceinline__ float3 mk3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float dot2(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float3 add3(float3 a, float3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 sub3(float3 a, float3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 scale3(float3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 mul3(float3 a, float3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return mk2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return mk2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 scale2(float2 a, float s) { return mk2(a.x * s, a.y * s); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// GLSL inversesqrt / normalize as the oracle defines them: 1/sqrt (both correctly rounded), then multiply
+__device__ __forceinline__ float inversesqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ float3 normalize3(float3 a) { return scale3(a, inversesqrt(dot3(a, a))); }
+__device__ __forceinline__ float2 normalize2(float2 a) { return scale2(a, inversesqrt(dot2(a, a))); }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float2 rotate_90(float2 v) { return mk2(-v.y, v.x); }

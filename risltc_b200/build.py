@@ -53,8 +53,12 @@ def build_host(force=False):
     deps = sources + list(HOST.glob("*.h")) + [PKG.parent / "include" / "risltc_cuda.h"]
     if force or _stale(HOST_LIB, deps):
         cmd = ["/usr/bin/gcc", "-std=c99", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
-               "-I", str(PKG.parent / "include"), "-I", str(HOST), "-o", str(HOST_LIB)] + [str(s) for s in sources] + ["-lm", "-ldl"]
+               "-I", str(PKG.parent / "include"), "-I", str(HOST), "-o", str(HOST_LIB)] + [str(s) for s in sources if s.name != "main.c"] + [
+                   "-L", str(PKG), "-lrisltc_cuda", "-Wl,-rpath,$ORIGIN", "-lm"]
         subprocess.check_call(cmd)
+        exe = ["/usr/bin/gcc", "-std=c99", "-O2", "-I", str(HOST), "-I", str(PKG.parent / "include"), "-o", str(PKG / "risltc"), str(HOST / "main.c"),
+               "-L", str(PKG), "-lrisltc_host", "-lrisltc_cuda", "-Wl,-rpath,$ORIGIN", "-lm"]
+        subprocess.check_call(exe)
     return HOST_LIB
 
 

@@ -67,6 +67,17 @@ int risltc_cuda_upload_ltc(risltc_device_t* device, const uint16_t* rgba16, cons
 /* change_shading / create_shading_pass (main.c:2498, 937-1010). */
 int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* variant);
 
+/* Arithmetic mode of the shading kernel. The reference compiles its GLSL without a precision contract
+ * (drivers contract a*b+c and use approximate rsqrt / rcp freely), so two modes are offered:
+ * RISLTC_PRECISION_FAST (default): fused multiply-adds, MUFU rsqrt / rcp, lights staged in shared memory;
+ * image within BASELINE.json's tolerance of the oracle (rel. RMSE <= 1e-3 converged, >= 99 % pixels).
+ * RISLTC_PRECISION_EXACT: every operation rounded like the C oracle (no contraction, IEEE div / sqrt);
+ * image bit-identical to the oracle up to libm ulps. Replaces nothing in the reference (its shader
+ * compiler decides); documented here because it selects between two compiled kernel sets. */
+#define RISLTC_PRECISION_FAST 0u
+#define RISLTC_PRECISION_EXACT 1u
+int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
+
 /* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
  * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index
  * (stripe_count = 1: the whole frame). Resets the accumulation buffer. */
@@ -97,7 +108,8 @@ int risltc_cuda_read_visibility(risltc_device_t* device, uint32_t* primitive_ids
 int risltc_cuda_owned_row_indices(const risltc_device_t* device, uint32_t* rows);
 
 /* record_frame_time (frame_timer.c:37-55): milliseconds of the last render_frame(s) call
- * (blocks until it has finished); per-kernel split in ms[4] = visibility, shading, shadow+accumulate, total. */
+ * (blocks until it has finished); ms[4] = visibility, shading, shadow+accumulate kernels summed
+ * over the frames of the call (CUDA events on the device's stream around every launch), and the whole call. */
 float risltc_cuda_last_frame_ms(risltc_device_t* device);
 int risltc_cuda_last_kernel_ms(risltc_device_t* device, float ms[4]);
 /* Counters of the last frame: [0] covered (non-background) pixel-samples, [1] shadow rays traced,

@@ -37,6 +37,9 @@ VARIANTS = {
     "ris_ltc_weighted_v3": dict(light="reservoir", tech="ltc_cp", mis="weighted", S=1, L=1, vmin=3, vmax=3),
     "ris_ltc_optimal_v3": dict(light="reservoir", tech="ltc_cp", mis="optimal", S=1, L=1, vmin=3, vmax=3),
     "uni_psa_biased_fast_v5": dict(light="uniform", tech="psa_biased", mis="power", S=1, L=1, fast_atan=1, vmin=3, vmax=5),
+    # control: the default variant compiled the way a GLSL compiler may compile it (a*b+c contracted to fma). Its
+    # distance to ris_ltc_v3 is the reference's own sensitivity to legal rounding changes (tests/test_gpu_frames.py).
+    "ris_ltc_v3_fma": dict(light="reservoir", tech="ltc_cp", mis="optimal_clamped", S=1, L=1, vmin=3, vmax=3, contract=True),
 }
 
 EXCLUDED_INCLUDES = {"cubic_solver.glsl", "srgb_utility.glsl"}   # unreachable from the shading pass
@@ -143,7 +146,8 @@ def build_shading(names=None, verbose=False):
         tu_path.write_text(tu)
         for name in (names or VARIANTS):
             out = OUT / f"libref_shading_{name}.so"
-            cmd = [CXX, "-std=gnu++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-shared", "-w",
+            contract = ["-ffp-contract=fast", "-mfma"] if VARIANTS[name].get("contract") else ["-ffp-contract=off"]
+            cmd = [CXX, "-std=gnu++17", "-O2"] + contract + ["-fno-fast-math", "-fopenmp", "-fPIC", "-shared", "-w",
                    "-I", str(HERE), f'-DREF_SHADER_TU="{tu_path}"'] + defines(VARIANTS[name]) + ["-o", str(out), str(HERE / "ref_harness.cpp")]
             if verbose:
                 print(" ".join(cmd))

@@ -140,16 +140,22 @@ def frame_words(frame_seed):
 class OracleScene:
     """Owns the numpy buffers behind an orc_scene_t and its BVH."""
 
-    def __init__(self, scene, ltc_rgba16, ltc_rg16, max_vertices=None):
-        from risltc_b200.scenes import material_constants
-        mesh = scene["mesh"]
+    def __init__(self, scene, ltc_rgba16, ltc_rg16, max_vertices=None, arrays=None):
+        """scene: a risltc_b200.scenes dict; or arrays = dict(positions, normals_uv, material_indices,
+        dequant_factor, dequant_summand, materials (M,8), records (N,12+4V), min_vertices) as stored in tests/golden."""
+        if arrays is None:
+            from risltc_b200.scenes import material_constants
+            mesh = scene["mesh"]
+            arrays = dict(mesh, materials=material_constants(scene["materials"]), records=light_records(scene["lights"], max_vertices),
+                          min_vertices=min(len(l["vertices_plane_space"]) for l in scene["lights"]))
+        mesh = arrays
         self.positions = np.ascontiguousarray(mesh["positions"], dtype=np.uint32)
         self.normals_uv = np.ascontiguousarray(mesh["normals_uv"], dtype=np.uint16)
         self.material_indices = np.ascontiguousarray(mesh["material_indices"], dtype=np.uint8)
-        self.materials = np.ascontiguousarray(material_constants(scene["materials"]), dtype=np.float32)
-        self.records = np.ascontiguousarray(light_records(scene["lights"], max_vertices))
+        self.materials = np.ascontiguousarray(arrays["materials"], dtype=np.float32)
+        self.records = np.ascontiguousarray(arrays["records"], dtype=np.float32)
         self.max_vertices = (self.records.shape[1] - 12) // 4
-        self.min_vertices = min(len(l["vertices_plane_space"]) for l in scene["lights"])
+        self.min_vertices = int(arrays["min_vertices"])
         self.rgba16 = np.ascontiguousarray(ltc_rgba16, dtype=np.uint16)
         self.rg16 = np.ascontiguousarray(ltc_rg16, dtype=np.uint16)
         s = Scene()
@@ -187,3 +193,71 @@ class OracleScene:
 
 def thread_count():
     return int(lib().orc_thread_count())
+
+
+# ---- function-level wrappers (same shapes as oracle/ref.py and the risltc_cuda_kat_* entry points)
+def clip_polygon(vertex_count, v, min_vertices, max_polygon_vertices):
+    buf = np.zeros((MAX_P, 3), dtype=np.float32); buf[:] = np.asarray(v, dtype=np.float32).reshape(MAX_P, 3)
+    vc = int(lib().orc_clip_polygon(C.c_uint32(vertex_count), _p(buf), C.c_uint32(min_vertices), C.c_uint32(max_polygon_vertices)))
+    return vc, buf
+
+
+def calculate_ltc(vertex_count, v):
+    buf = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(MAX_P, 3))
+    return float(lib().orc_calculate_ltc(C.c_uint32(vertex_count), _p(buf)))
+
+
+def psa(vertex_count, v, u0, u1, max_polygon_vertices, fast_atan=0, biased=0):
+    """Returns (44 floats {vc, v[8][2], e[8][2], inner0[2], sectors[8], total}, sampled direction)."""
+    buf = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(MAX_P, 3))
+    poly = PsaPolygon()
+    lib().orc_prepare_psa(C.byref(poly), C.c_uint32(vertex_count), _p(buf), C.c_uint32(max_polygon_vertices), C.c_uint32(fast_atan))
+    d = np.zeros(3, dtype=np.float32)
+    lib().orc_sample_psa(_p(d), C.byref(poly), C.c_float(u0), C.c_float(u1), C.c_uint32(max_polygon_vertices), C.c_uint32(fast_atan), C.c_uint32(biased))
+    out = np.zeros(44, dtype=np.float32)
+    out[0] = poly.vertex_count
+    for k in range(min(vertex_count, MAX_P)):
+        out[1 + 2 * k], out[2 + 2 * k] = poly.vertices[k][0], poly.vertices[k][1]
+        out[17 + 2 * k], out[18 + 2 * k] = poly.ellipses[k][0], poly.ellipses[k][1]
+        out[35 + k] = poly.sector_projected_solid_angles[k]
+    out[33], out[34] = poly.inner_ellipse_0[0], poly.inner_ellipse_0[1]
+    out[43] = poly.projected_solid_angle
+    return out, d
+
+
+def ltc_coefficients(oscene, fresnel_0, roughness, pos, normal, outgoing, constants6):
+    """32 floats: world_to_shading[12] (column-major), shading_to_cosine[9], cosine_to_shading[9], albedo, determinant."""
+    l = Ltc()
+    f3 = lambda a: (C.c_float * 3)(*[float(x) for x in a])
+    lib().orc_get_ltc_coefficients(C.byref(l), C.byref(oscene.c), C.c_float(fresnel_0), C.c_float(roughness), f3(pos), f3(normal), f3(outgoing),
+                                   (C.c_float * 6)(*[float(x) for x in constants6]))
+    out = np.zeros(32, dtype=np.float32)
+    out[0:12] = np.array([list(col) for col in l.world_to_shading], dtype=np.float32).reshape(-1)
+    out[12:21] = np.array([list(col) for col in l.shading_to_cosine], dtype=np.float32).reshape(-1)
+    out[21:30] = np.array([list(col) for col in l.cosine_to_shading], dtype=np.float32).reshape(-1)
+    out[30], out[31] = l.albedo, l.determinant
+    return out
+
+
+def noise(px, py, width, frame_word, draws):
+    seed = C.c_uint32(lib().orc_noise_seed(C.c_uint32(px), C.c_uint32(py), C.c_uint32(width), C.c_uint32(frame_word)))
+    return np.array([lib().orc_noise_next(C.byref(seed)) for _ in range(draws)], dtype=np.float32)
+
+
+def update_light(light):
+    """(world (n,4), plane (4,), surface_radiance (3,), area) of polygonal_light.c:44-98."""
+    n = len(light["vertices_plane_space"])
+    ps = np.zeros((n, 4), dtype=np.float32); ps[:, :2] = np.asarray(light["vertices_plane_space"], dtype=np.float32)[:, :2]
+    world = np.zeros((n, 4), dtype=np.float32)
+    plane = (C.c_float * 4)(); rad = (C.c_float * 3)(); area = C.c_float()
+    lib().orc_update_polygonal_light((C.c_float * 3)(*light["rotation_angles"]), C.c_float(light["scaling_x"]), C.c_float(light["scaling_y"]),
+                                     (C.c_float * 3)(*light["translation"]), (C.c_float * 3)(*light["radiant_flux"]), C.c_uint32(n),
+                                     _p(ps), _p(world), plane, rad, C.byref(area), None)
+    return world, np.array(list(plane), dtype=np.float32), np.array(list(rad), dtype=np.float32), float(area.value)
+
+
+def world_to_projection(cam, aspect):
+    out = ((C.c_float * 4) * 4)()
+    lib().orc_world_to_projection(out, (C.c_float * 3)(*cam["position"]), C.c_float(cam["rotation_x"]), C.c_float(cam["rotation_z"]),
+                                  C.c_float(cam["vertical_fov"]), C.c_float(cam["near"]), C.c_float(cam["far"]), C.c_float(aspect))
+    return np.array([list(r) for r in out], dtype=np.float32)

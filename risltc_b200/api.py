@@ -97,6 +97,9 @@ class Device:
     def set_variant(self, var):
         _check(lib().risltc_cuda_set_variant(self.h, C.byref(var)))
 
+    def set_precision(self, mode):
+        _check(lib().risltc_cuda_set_precision(self.h, C.c_uint32({"fast": 0, "exact": 1}[mode])))
+
     def resize(self, width, height, stripe_height=8, stripe_index=0, stripe_count=1):
         _check(lib().risltc_cuda_resize(self.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(stripe_height),
                                         C.c_uint32(stripe_index), C.c_uint32(stripe_count)))

@@ -14,12 +14,11 @@ HOST = PKG / "host"
 CUDA_LIB = PKG / "librisltc_cuda.so"
 HOST_LIB = PKG / "librisltc_host.so"
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    # IEEE arithmetic as written: no a*b+c contraction (parity with the fp32 oracle), exact div / sqrt
-    "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared",
-]
+NVCC_COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off"]
+# `exact` kernel set (api.cu): IEEE arithmetic as written, no a*b+c contraction -> rounding identical to the fp32 oracle
+NVCC_EXACT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+# `fast` kernel set (fast.cu): what a GLSL compiler is free to do -- contraction, MUFU rcp / rsqrt / sqrt, flush-to-zero
+NVCC_FAST = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 
 
 def _nvcc():
@@ -37,12 +36,22 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    sources = [CSRC / "api.cu", CSRC / "bvh_build.cpp"]
-    deps = sources + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [PKG.parent / "include" / "risltc_cuda.h"]
+    units = [(CSRC / "api.cu", NVCC_EXACT), (CSRC / "fast.cu", NVCC_FAST), (CSRC / "bvh_build.cpp", [])]
+    deps = [u for u, _ in units] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [PKG.parent / "include" / "risltc_cuda.h"]
     if force or _stale(CUDA_LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(CUDA_LIB)] + [str(s) for s in sources]
         env = {**os.environ, "CC": "gcc", "CXX": "g++"}
-        subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+        objdir = PKG / "build"
+        objdir.mkdir(exist_ok=True)
+        procs, objs = [], []
+        for src, flags in units:
+            obj = objdir / (src.stem + ".o")
+            objs.append(str(obj))
+            cmd = [_nvcc()] + NVCC_COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", str(obj), str(src), "-ccbin", "/usr/bin/g++"]
+            procs.append((cmd, subprocess.Popen(cmd, env=env)))
+        for cmd, p in procs:
+            if p.wait() != 0:
+                raise subprocess.CalledProcessError(p.returncode, cmd)
+        subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB)] + objs + ["-ccbin", "/usr/bin/g++"], env=env)
     return CUDA_LIB
 
 

@@ -2,11 +2,14 @@
 #include "../../include/risltc_cuda.h"
 #include "kernels.cuh"
 #include "bvh_build.h"
+#include "launch.h"
 #include "clip_rotation_table.inc"
 #include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
+
+using namespace exact;
 
 static thread_local std::string g_last_error;
 
@@ -20,10 +23,10 @@ static int fail(const char* what, const char* detail) {
 struct risltc_device_s {
 	int ordinal = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // batch start, after (1), after (2), after (3+4) of last frame, batch end
+	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // [0] batch start, [4] batch end
 	// scene
 	uint2* positions = nullptr; ushort4* normals_uv = nullptr; uint8_t* material_indices = nullptr;
-	float4* materials = nullptr; float4* lights = nullptr; ushort4* ltc_rgba = nullptr; ushort2* ltc_rg = nullptr;
+	float4* materials = nullptr; float4* lights = nullptr; float4* lights_tri = nullptr; ushort4* ltc_rgba = nullptr; ushort2* ltc_rg = nullptr;
 	BvhNode* nodes = nullptr; BvhTri* tris = nullptr;
 	SceneView view = {};
 	float dequant_factor[3] = { 0, 0, 0 }, dequant_summand[3] = { 0, 0, 0 };
@@ -34,8 +37,12 @@ struct risltc_device_s {
 	PixelBuffers px = {};
 	float4* own_accum = nullptr;
 	uint32_t ray_slots = 0, group_slots = 0;
+	uint32_t precision = RISLTC_PRECISION_FAST;
 	unsigned long long launches = 0;
 	bool timed = false;
+	// per-frame events of the last batch: 4 per frame (before (1), after (1), after (2), after (3+4))
+	std::vector<cudaEvent_t> frame_events;
+	uint32_t timed_frames = 0;
 };
 
 static int use(risltc_device_t* d) {
@@ -62,6 +69,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
 	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
+	CU(fast::initialize(cuda_ordinal));
 	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
 	*device = d;
@@ -86,8 +94,9 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	cudaSetDevice(d->ordinal);
 	if (d->stream) cudaStreamSynchronize(d->stream);
 	free_targets(d); free_scene(d);
-	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters);
+	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters);
 	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
+	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
 	delete d;
 }
@@ -166,9 +175,24 @@ extern "C" int risltc_cuda_upload_lights(risltc_device_t* d, const void* records
 	if (d->view.light_count != light_count || d->view.light_stride4 != 3 + max_vertex_count) {
 		CU(cudaStreamSynchronize(d->stream));
 		cudaFree(d->lights); d->lights = nullptr;
+		cudaFree(d->lights_tri); d->lights_tri = nullptr;
 		CU(cudaMalloc(&d->lights, bytes));
+		if (max_vertex_count == 3) CU(cudaMalloc(&d->lights_tri, (size_t) light_count * 48));
 	}
 	CU(cudaMemcpyAsync(d->lights, records, bytes, cudaMemcpyHostToDevice, d->stream));
+	if (max_vertex_count == 3) {
+		// the candidate loop's view of a triangle light: 48 bytes {v0 | Le.r, v1 | Le.g, v2 | Le.b}
+		const float* r = (const float*) records;
+		std::vector<float> packed((size_t) light_count * 12);
+		for (uint32_t i = 0; i != light_count; ++i, r += 24)
+			for (int v = 0; v != 3; ++v) {
+				memcpy(&packed[12 * (size_t) i + 4 * v], r + 12 + 4 * v, 12);
+				packed[12 * (size_t) i + 4 * v + 3] = r[v];
+			}
+		CU(cudaMemcpyAsync(d->lights_tri, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+		CU(cudaStreamSynchronize(d->stream));   // `packed` is pageable stack-owned memory
+	}
+	d->view.lights_tri = d->lights_tri;
 	d->view.lights = d->lights; d->view.light_count = light_count; d->view.light_stride4 = 3 + max_vertex_count;
 	return 0;
 }
@@ -216,6 +240,14 @@ extern "C" int risltc_cuda_set_variant(risltc_device_t* d, const risltc_variant_
 	CU(cudaStreamSynchronize(d->stream));
 	memcpy(&d->variant, v, sizeof(Variant));
 	return allocate_ray_buffers(d);
+}
+
+extern "C" int risltc_cuda_set_precision(risltc_device_t* d, uint32_t mode) {
+	if (use(d)) return 1;
+	if (mode > RISLTC_PRECISION_EXACT) return fail("set_precision: unknown mode", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	d->precision = mode;
+	return 0;
 }
 
 extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t height, uint32_t stripe_height, uint32_t stripe_index, uint32_t stripe_count) {
@@ -288,18 +320,22 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	const bool defer = d->variant.polygon_technique != TECH_TURK && d->variant.polygon_technique != TECH_BASELINE && d->variant.mis_heuristic != MIS_OPTIMAL;
 	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
 	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
+	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
+	d->timed_frames = frame_count;
 	CU(cudaEventRecord(d->ev[0], d->stream));
 	for (uint32_t i = 0; i != frame_count; ++i) {
 		FrameUniforms f;
 		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
-		bool last = (i + 1 == frame_count);
+		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
+		if (d->precision == RISLTC_PRECISION_FAST) { fast::launch_frame(d->stream, d->view, f, d->variant, d->stripes, d->px, fe); d->launches += 3; continue; }
+		CU(cudaEventRecord(fe[0], d->stream));
 		gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
-		if (last) CU(cudaEventRecord(d->ev[1], d->stream));
+		CU(cudaEventRecord(fe[1], d->stream));
 		if (d->variant.max_light_vertices == 3) launch_shade<3>(d, grid, f, defer); else launch_shade<4>(d, grid, f, defer);
-		if (last) CU(cudaEventRecord(d->ev[2], d->stream));
+		CU(cudaEventRecord(fe[2], d->stream));
 		resolve_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
-		if (last) CU(cudaEventRecord(d->ev[3], d->stream));
+		CU(cudaEventRecord(fe[3], d->stream));
 		d->launches += 3;
 	}
 	CU(cudaEventRecord(d->ev[4], d->stream));
@@ -344,13 +380,12 @@ extern "C" int risltc_cuda_last_kernel_ms(risltc_device_t* d, float ms[4]) {
 	if (use(d)) return 1;
 	if (!d->timed) return fail("last_kernel_ms: no frame rendered yet", nullptr);
 	CU(cudaEventSynchronize(d->ev[4]));
-	float lead = 0.0f;
-	CU(cudaEventElapsedTime(&ms[0], d->ev[0], d->ev[1]));   // includes earlier frames of a batch; corrected below
-	CU(cudaEventElapsedTime(&ms[1], d->ev[1], d->ev[2]));
-	CU(cudaEventElapsedTime(&ms[2], d->ev[2], d->ev[3]));
+	ms[0] = ms[1] = ms[2] = 0.0f;
+	for (uint32_t i = 0; i != d->timed_frames; ++i) {
+		const cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
+		for (int k = 0; k != 3; ++k) { float t = 0.0f; CU(cudaEventElapsedTime(&t, fe[k], fe[k + 1])); ms[k] += t; }
+	}
 	CU(cudaEventElapsedTime(&ms[3], d->ev[0], d->ev[4]));
-	CU(cudaEventElapsedTime(&lead, d->ev[0], d->ev[3]));
-	(void) lead;
 	return 0;
 }
 

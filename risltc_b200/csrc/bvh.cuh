@@ -12,6 +12,8 @@
 #pragma once
 #include "common.cuh"
 
+namespace RL_NS {
+
 #define RL_STACK 64
 
 __device__ __forceinline__ float xdot3(float3 a, float3 b) {
@@ -139,3 +141,5 @@ __device__ uint32_t bvh_closest_front(const SceneView& s, float3 o, float3 d, co
 		else return best;
 	}
 }
+
+}  // namespace RL_NS

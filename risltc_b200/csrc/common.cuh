@@ -4,6 +4,16 @@
 #include <stdint.h>
 #include <math.h>
 
+// Two translation units compile the same kernels: api.cu as namespace `exact` (no contraction, IEEE
+// div / sqrt: every rounding as in the C oracle) and fast.cu as namespace `fast` (RL_FAST: fused
+// multiply-adds, MUFU rsqrt / rcp, flush-to-zero). Host-visible structs are shared.
+#ifndef RL_NS
+#define RL_NS exact
+#endif
+#ifndef RL_FAST
+#define RL_FAST 0
+#endif
+
 #define RL_MAX_P 8            // largest MAX_POLYGON_VERTEX_COUNT (V_max 7 + 1, main.c:191-204)
 #define RL_PI 3.14159265358979323846f
 #define RL_HALF_PI 1.57079632679489661923f
@@ -57,11 +67,25 @@ struct SceneView {
 	const uint8_t* material_indices; // T
 	const float4* materials;         // 2 float4 per material: {base rgb, occlusion}, {roughness_lin, metalicity, normal.r, normal.g}
 	const float4* lights;            // light records, (3 + V) float4 each
+	const float4* lights_tri;        // triangle lights repacked as 3 float4 {v0 | Le.r, v1 | Le.g, v2 | Le.b}, or null
 	uint32_t light_count, light_stride4;
 	const ushort4* ltc_rgba; const ushort2* ltc_rg; uint32_t ltc_res, ltc_layers;
 	const BvhNode* nodes; const BvhTri* tris; uint32_t triangle_count;
 };
 
+struct PixelBuffers {
+	uint32_t* visibility;   // [owned_rows * W] primitive id | emitter << 31, 0xFFFFFFFF = background
+	float4* origin;         // [pixels] shading position, .w = bits of (number of light-sample groups)
+	float4* base;           // [pixels] colour that needs no ray (background, emitters, inline variants)
+	float4* group;          // [L][pixels] {carry rgb, scale}: sum of terms that need no ray, factor W (or N) of the group
+	float4* ray_a;          // [L*S*2][pixels] {dir xyz, t_max}
+	float4* ray_b;          // [L*S*2][pixels] {term rgb, valid}
+	float4* accum;          // [pixels] RGBA32F running mean
+	unsigned long long* counters;   // [0] shaded pixels, [1] rays traced, [3] candidates
+	uint32_t pixel_count;
+};
+
+namespace RL_NS {
 // ---- tiny vector helpers (no operator overloading on purpose: every rounding is visible)
 __device__ __forceinline__ float3 mk3(float x, float y, float z) { return make_float3(x, y, z); }
 __device__ __forceinline__ float2 mk2(float x, float y) { return make_float2(x, y); }
@@ -76,8 +100,13 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return mk2(a.x - b.
 __device__ __forceinline__ float2 scale2(float2 a, float s) { return mk2(a.x * s, a.y * s); }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // GLSL inversesqrt / normalize as the oracle defines them: 1/sqrt (both correctly rounded), then multiply
+#if RL_FAST
+__device__ __forceinline__ float inversesqrt(float x) { return rsqrtf(x); }   // one MUFU.RSQ
+#else
 __device__ __forceinline__ float inversesqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
 __device__ __forceinline__ float3 normalize3(float3 a) { return scale3(a, inversesqrt(dot3(a, a))); }
 __device__ __forceinline__ float2 normalize2(float2 a) { return scale2(a, inversesqrt(dot2(a, a))); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float2 rotate_90(float2 v) { return mk2(-v.y, v.x); }
+}  // namespace RL_NS

@@ -9,17 +9,8 @@
 #include "shading.cuh"
 #include "bvh.cuh"
 
-struct PixelBuffers {
-	uint32_t* visibility;   // [owned_rows * W] primitive id | emitter << 31, 0xFFFFFFFF = background
-	float4* origin;         // [pixels] shading position, .w = bits of (number of light-sample groups)
-	float4* base;           // [pixels] colour that needs no ray (background, emitters, inline variants)
-	float4* group;          // [L][pixels] {carry rgb, scale}: sum of terms that need no ray, factor W (or N) of the group
-	float4* ray_a;          // [L*S*2][pixels] {dir xyz, t_max}
-	float4* ray_b;          // [L*S*2][pixels] {term rgb, valid}
-	float4* accum;          // [pixels] RGBA32F running mean
-	unsigned long long* counters;   // [0] shaded pixels, [1] rays traced, [3] candidates
-	uint32_t pixel_count;
-};
+namespace RL_NS {
+
 
 __device__ __forceinline__ bool tile_pixel(const FrameUniforms& f, const Stripes& st, uint32_t& x, uint32_t& local_row, uint32_t& y) {
 	uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -274,3 +265,5 @@ __global__ void __launch_bounds__(128) resolve_kernel(SceneView s, FrameUniforms
 	unsigned warp_rays = __reduce_add_sync(active, rays);
 	if ((threadIdx.x & 31u) == (unsigned) (__ffs(active) - 1) && warp_rays) atomicAdd(&out.counters[1], (unsigned long long) warp_rays);
 }
+
+}  // namespace RL_NS

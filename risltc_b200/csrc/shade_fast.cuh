@@ -1,0 +1,161 @@
+// shade_fast.cuh -- the fused RIS + shading kernel specialised for the default estimator
+// ("ours", main.c:220-236): light_reservoir with m = 32 candidates whose target function is the
+// analytic LTC integral (shading_pass.frag.glsl:723-761, :430-456) over TRIANGLE lights, winner
+// shaded by projected-solid-angle + LTC-warped samples combined with optimal-clamped MIS
+// (:292-397). Compiled only in the `fast` translation unit.
+//
+// What differs from the generic kernel (kernels.cuh) is organisation, not the algorithm:
+//  * persistent CTAs (grid = SMs x resident CTAs) walk 16x8 pixel tiles; the light table is staged
+//    ONCE per CTA into shared memory as 48-byte records {v0 | Le.r, v1 | Le.g, v2 | Le.b} and the
+//    32 random candidates of every pixel are gathered from there with three LDS.128;
+//  * the candidate needs no plane equation: flipping the shading frame's y row mirrors the polygon,
+//    which negates the signed edge sum exactly and calculate_ltc takes abs() (polygon_sampling.glsl:529);
+//  * cosine-space vertices come from the shading-space ones through the 5 non-zeros of
+//    shading_to_cosine_space instead of a second 4x3 transform of the world-space vertices;
+//  * horizon clipping of a triangle is a register-only case split (all above / all below / one or
+//    two vertices above), only the mixed cases take the slow path;
+//  * r < w / w_sum is tested as r * w_sum < w; the reservoir stays strictly sequential per pixel, so
+//    the random stream and the prefix sums keep the reference's order.
+#pragma once
+#include "kernels.cuh"
+
+namespace RL_NS {
+
+__device__ __forceinline__ float ff_edge(float3 a, float3 b) {   // integrateEdgeVec on unit vectors
+	float x = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), y = fabsf(x);
+	float num = fmaf(fmaf(0.0145206f, y, 0.4965155f), y, 0.8543985f);
+	float den = fmaf(4.1616724f + y, y, 3.4175940f);
+	float v = __fdividef(num, den);
+	float alt = fmaf(0.5f, rsqrtf(fmaxf(fmaf(-x, x, 1.0f), 1e-7f)), -v);
+	float t = (x > 0.0f) ? v : alt;
+	return fmaf(a.x, b.y, -a.y * b.x) * t;
+}
+__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, rsqrtf(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z)))); }
+
+// Mixed horizon cases of a triangle: 1 vertex above -> triangle, 2 above -> quad (polygon_clipping.glsl:35-225
+// restricted to vertex_count == 3). Registers only.
+__device__ __noinline__ float ff_clipped_triangle(float3 p0, float3 p1, float3 p2, uint32_t mask) {
+	// rotate so that (A, B, C) is cyclic with A the lone vertex above (one above) or C the lone vertex below (two above)
+	bool one = (mask == 1u || mask == 2u || mask == 4u);
+	uint32_t key = one ? mask : (7u ^ mask);           // the odd vertex out
+	float3 A, B, C;                                     // odd vertex -> slot `odd`, successors follow
+	if (key == 1u) { A = p0; B = p1; C = p2; }
+	else if (key == 2u) { A = p1; B = p2; C = p0; }
+	else { A = p2; B = p0; C = p1; }
+	// A is the odd one out: crossings on AB and CA
+	float3 iab = horizon_crossing(A, B), ica = horizon_crossing(C, A);
+	float sum;
+	if (one) {
+		float3 a = unit3(A), b = unit3(iab), c = unit3(ica);
+		sum = ff_edge(a, b) + ff_edge(b, c) + ff_edge(c, a);
+	}
+	else {
+		// A below: polygon B, C, crossing CA, crossing AB
+		float3 b = unit3(B), c = unit3(C), d = unit3(ica), e = unit3(iab);
+		sum = ff_edge(b, c) + ff_edge(c, d) + ff_edge(d, e) + ff_edge(e, b);
+	}
+	return fabsf(sum);
+}
+
+// |calculate_ltc| of a triangle clipped to z >= 0
+__device__ __forceinline__ float ff_triangle(float3 p0, float3 p1, float3 p2) {
+	uint32_t mask = (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
+	float result = 0.0f;
+	if (mask == 7u) {
+		float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
+		result = fabsf(ff_edge(a, b) + ff_edge(b, c) + ff_edge(c, a));
+	}
+	else if (mask != 0u) result = ff_clipped_triangle(p0, p1, p2, mask);
+	return result;
+}
+
+#define RL_FAST_MIN_BLOCKS 3
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) shade_ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+	extern __shared__ float4 sm_lights[];
+	const int N = (int) s.light_count;
+	if (SMEM) {
+		for (uint32_t i = threadIdx.x; i < 3u * (uint32_t) N; i += blockDim.x) sm_lights[i] = __ldg(&s.lights_tri[i]);
+		__syncthreads();
+	}
+	const float4* table = SMEM ? sm_lights : s.lights_tri;
+	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t shaded = 0;
+	for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x) {
+		const uint32_t x = (tile % tiles_x) * 16u + (warp & 1u) * 8u + (lane & 7u);
+		const uint32_t row = (tile / tiles_x) * 8u + (warp >> 1) * 4u + (lane >> 3);
+		if (x >= f.width || row >= st.owned_rows) continue;
+		const uint32_t y = st.global_row(row);
+		if (y >= f.height) continue;
+		const uint32_t pixel = row * f.width + x;
+		const uint32_t prim = out.visibility[pixel];
+		if (prim == 0xFFFFFFFFu || (prim >> 31) != 0u) {
+			float v = (prim == 0xFFFFFFFFu) ? 0.0f : 1.0f;
+			out.base[pixel] = make_float4(v, v, v, (prim == 0xFFFFFFFFu) ? 1.0f : 0.0f);
+			out.origin[pixel] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+			continue;
+		}
+		++shaded;
+		ShadingPoint sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
+		float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+		LtcFrame ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+		uint32_t seed = noise_seed(x, y, f.width, f.frame_word);
+		// ---- RIS over 32 candidates
+		const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
+		float w_sum = 0.0f, chosen_p_hat = 0.0f;
+		int chosen = -1;
+		#pragma unroll 2
+		for (int i = 0; i != 32; ++i) {
+			seed = 1664525u * seed + 1013904223u;
+			int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
+			const float4 A = table[3 * idx], B = table[3 * idx + 1], C = table[3 * idx + 2];
+			float3 p0, p1, p2;
+			p0.x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
+			p0.y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
+			p0.z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
+			p1.x = fmaf(ltc.rx.x, B.x, fmaf(ltc.rx.y, B.y, fmaf(ltc.rx.z, B.z, ltc.t.x)));
+			p1.y = fmaf(ltc.ry.x, B.x, fmaf(ltc.ry.y, B.y, fmaf(ltc.ry.z, B.z, ltc.t.y)));
+			p1.z = fmaf(ltc.rz.x, B.x, fmaf(ltc.rz.y, B.y, fmaf(ltc.rz.z, B.z, ltc.t.z)));
+			p2.x = fmaf(ltc.rx.x, C.x, fmaf(ltc.rx.y, C.y, fmaf(ltc.rx.z, C.z, ltc.t.x)));
+			p2.y = fmaf(ltc.ry.x, C.x, fmaf(ltc.ry.y, C.y, fmaf(ltc.ry.z, C.z, ltc.t.y)));
+			p2.z = fmaf(ltc.rz.x, C.x, fmaf(ltc.rz.y, C.y, fmaf(ltc.rz.z, C.z, ltc.t.z)));
+			float fd = ff_triangle(p0, p1, p2);
+			float3 q0 = mk3(fmaf(ltc.s00, p0.x, ltc.s02 * p0.z), ltc.s11 * p0.y, fmaf(ltc.s20, p0.x, ltc.s22 * p0.z));
+			float3 q1 = mk3(fmaf(ltc.s00, p1.x, ltc.s02 * p1.z), ltc.s11 * p1.y, fmaf(ltc.s20, p1.x, ltc.s22 * p1.z));
+			float3 q2 = mk3(fmaf(ltc.s00, p2.x, ltc.s02 * p2.z), ltc.s11 * p2.y, fmaf(ltc.s20, p2.x, ltc.s22 * p2.z));
+			float fs = ff_triangle(q0, q1, q2) * ltc.albedo;
+			float cr = fmaf(sp.diffuse_albedo.x, fd, fs) * A.w, cg = fmaf(sp.diffuse_albedo.y, fd, fs) * B.w, cb = fmaf(sp.diffuse_albedo.z, fd, fs) * C.w;
+			float p_hat = sqrtf(fmaf(cr, cr, fmaf(cg, cg, cb * cb)));
+			float w = p_hat * Nf;
+			seed = 1664525u * seed + 1013904223u;
+			float r = __uint2float_rn(seed) * 2.3283064365386962890625e-10f;
+			w_sum += w;
+			if (w > 0.0f && r * w_sum < w) { chosen = idx; chosen_p_hat = p_hat; }
+		}
+		// ---- the winner: evaluate_polygonal_light_shading_peters, rays deferred to the resolve kernel
+		float scale = 0.0f;
+		float3 carry = mk3(0.0f, 0.0f, 0.0f);
+		uint32_t rays = 0;
+		if (chosen >= 0) {
+			Light<3> light = load_light<3>(s, (uint32_t) chosen);
+			scale = (chosen_p_hat == 0.0f) ? 0.0f : w_sum / (32.0f * chosen_p_hat);
+			ShadeContext<3, true> c = { s, f, var, out, pixel, seed, 0u };
+			carry = sample_light<3, true>(c, sp, ltc, light, true, false, 0u);
+			rays = c.rays;
+		}
+		(void) rays;
+		out.group[pixel] = make_float4(carry.x, carry.y, carry.z, scale);
+		out.base[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
+	}
+	// counters: one atomic per warp at the end of the CTA's life
+	unsigned total = __reduce_add_sync(0xFFFFFFFFu, shaded);
+	if (lane == 0 && total) {
+		atomicAdd(&out.counters[0], (unsigned long long) total);
+		atomicAdd(&out.counters[3], 32ull * total);
+	}
+}
+
+}  // namespace RL_NS

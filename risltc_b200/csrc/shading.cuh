@@ -10,6 +10,8 @@
 #pragma once
 #include "common.cuh"
 
+namespace RL_NS {
+
 // rot[n - 3][above_mask]: slot order of the clipped polygon (tools/gen_clip_table.py)
 __constant__ unsigned char c_clip_rotation[5][128];
 
@@ -670,3 +672,5 @@ __device__ __forceinline__ float light_area_012(const Light<V>& l) {
 	float3 c = mk3(kahan(a.y, b.z, a.z, b.y), kahan(a.z, b.x, a.x, b.z), kahan(a.x, b.y, a.y, b.x));
 	return sqrtf(dot3(c, c)) / 2.0f;
 }
+
+}  // namespace RL_NS

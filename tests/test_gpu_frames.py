@@ -1,4 +1,9 @@
-"""-m gpu: whole-frame parity of the CUDA path (through the C ABI) against the CPU oracle."""
+"""-m gpu: whole-frame parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Two kernel sets are checked (include/risltc_cuda.h, risltc_cuda_set_precision):
+  exact -- every rounding as in the oracle: images agree to the last libm ulp, visibility bit for bit;
+  fast  -- the production set (FMA contraction, MUFU rsqrt / rcp): BASELINE.json's tolerance, i.e.
+           per-frame relative RMSE <= 1e-3 once converged and >= 99 % per-pixel agreement at matched spp."""
 import numpy as np
 import pytest
 
@@ -7,42 +12,136 @@ from tests.util import constants_bytes, image_metrics, setup_device
 pytestmark = pytest.mark.gpu
 
 
-def _render_both(device, scene, ltc_tables, ovar, gvar, width, height, frames, **ckw):
+def _render_both(device, scene, ltc_tables, ovar, gvar, width, height, frames, precision="exact", **ckw):
     from oracle import orc
     _, rgba, rg = ltc_tables
     osc = orc.OracleScene(scene, rgba, rg)
     cs = [orc.make_constants(scene, width, height, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0], **ckw) for f in range(frames)]
     ref, ref_vis, ref_rays = osc.render(cs, ovar)
     setup_device(device, scene, rgba, rg, gvar, width, height, osc.records)
+    device.set_precision(precision)
     device.render_frames(constants_bytes(cs))
     got = device.read_accum()
     vis = device.read_visibility()
     return ref, ref_vis, ref_rays, got, vis, device.counters()
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
 @pytest.mark.parametrize("light_sampling,technique", [("uniform", "projected_solid_angle"), ("reservoir", "ltc_cp")])
-def test_quad_over_plane(device, ltc_tables, light_sampling, technique):
+def test_quad_over_plane(device, ltc_tables, light_sampling, technique, precision):
     """BASELINE.json configs[0] at reduced size: single quad light over a diffuse plane."""
     from oracle import orc
     from risltc_b200 import api, scenes
     scene = scenes.quad_over_plane(320, 180)
     kw = dict(light_sampling=light_sampling, technique=technique, min_vertices=4, max_vertices=4)
-    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 320, 180, 1)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 320, 180, 1, precision)
     assert np.array_equal(vis, ref_vis), "primary visibility must be bit-exact"
     rmse, agree = image_metrics(got, ref)
-    print(f"quad {light_sampling}/{technique}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
+    print(f"quad {light_sampling}/{technique}/{precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
     assert rmse <= 1e-3 and agree >= 0.99
 
 
-@pytest.mark.parametrize("frames", [1, 4])
-def test_room_default_variant(device, ltc_tables, frames):
-    """The default estimator (RIS over LTC integrals -> PSA + LTC MIS) on a 64-light room."""
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("frames", [1, 4, 16])
+def test_room_default_variant(device, ltc_tables, frames, precision):
+    """The default estimator (RIS over LTC integrals -> PSA + LTC MIS) on a 64-light room; 16 frames = C2's spp."""
     from oracle import orc
     from risltc_b200 import api, scenes
     scene = scenes.many_light_room(64, 50, width=320, height=180)
-    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), 320, 180, frames)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), 320, 180, frames, precision)
     assert np.array_equal(vis, ref_vis), "primary visibility must be bit-exact"
     rmse, agree = image_metrics(got, ref)
-    print(f"room frames={frames}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
+    print(f"room frames={frames} {precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
     assert agree >= 0.99
-    assert rmse <= (1e-3 if frames > 1 else 5e-2)
+    # a single flipped reservoir decision changes one pixel of a 1-spp frame completely; the RMSE bound of
+    # BASELINE.json is for the converged (accumulated) frame
+    assert rmse <= (1e-3 if frames >= 16 else 5e-2)
+    assert counters["candidates"] == 32 * counters["shaded_pixels"]
+
+
+VARIANTS = [
+    dict(light_sampling="uniform"),
+    dict(technique="projected_solid_angle"),
+    dict(technique="area_turk"),
+    dict(light_sampling="uniform", technique="area_turk"),
+    dict(technique="projected_solid_angle", mis="balance", sample_count=2, light_samples=2),
+    dict(mis="weighted"),
+    dict(mis="optimal"),
+    dict(mis="power", technique="projected_solid_angle_biased", fast_atan=1),
+    dict(min_vertices=4, max_vertices=4),
+]
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("kw", VARIANTS, ids=lambda k: "-".join(f"{a}={b}" for a, b in k.items()))
+def test_room_variants(device, ltc_tables, kw, precision):
+    """The other shader variants of the comparison matrix (experiment_list.c:316-396)."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    verts = kw.get("max_vertices", 3)
+    scene = scenes.many_light_room(24, 30, seed=4, width=256, height=144, vertex_count=verts)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 256, 144, 2, precision)
+    assert np.array_equal(vis, ref_vis)
+    rmse, agree = image_metrics(got, ref)
+    print(f"variant {kw} {precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
+    assert agree >= 0.99 and rmse <= 5e-2
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_stripes_equal_whole_frame(device, ltc_tables, precision):
+    """any image partition gives the single-device image bit for bit."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    _, rgba, rg = ltc_tables
+    W, H = 200, 123     # neither a multiple of the tile nor of the stripe height
+    scene = scenes.many_light_room(32, 20, seed=6, width=W, height=H)
+    osc = orc.OracleScene(scene, rgba, rg)
+    cs = constants_bytes([orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0]) for f in range(2)])
+    setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records)
+    device.set_precision(precision)
+    device.render_frames(cs)
+    whole = device.read_accum()
+    assembled = np.zeros_like(whole)
+    for index in range(3):
+        device.resize(W, H, 8, index, 3)
+        device.render_frames(cs)
+        rows = device.owned_row_indices()
+        assembled[rows] = device.read_accum()
+    device.resize(W, H, 8, 0, 1)
+    assert np.array_equal(assembled.view(np.uint32), whole.view(np.uint32))
+
+
+def test_full_size_properties(device, ltc_tables):
+    """BASELINE.json configs[1] at full size (1920x1080, 64 lights), checked through size-independent properties:
+    determinism, accumulation = running mean of single frames, background / emitter pixels, fast vs exact agreement."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    _, rgba, rg = ltc_tables
+    W, H = 1920, 1080
+    scene = scenes.many_light_room(64, 200, seed=2, width=W, height=H)
+    records = orc.light_records(scene["lights"])
+    cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0]) for f in range(3)]
+    setup_device(device, scene, rgba, rg, api.variant(), W, H, records)
+    images = {}
+    for precision in ("exact", "fast"):
+        device.set_precision(precision)
+        device.render_frames(constants_bytes(cs))
+        a = device.read_accum()
+        device.render_frames(constants_bytes(cs))
+        assert np.array_equal(a.view(np.uint32), device.read_accum().view(np.uint32)), "not deterministic"
+        singles = []
+        for c in cs:
+            device.render_frames(constants_bytes([c]))
+            singles.append(device.read_accum())
+        mean = singles[0].copy()
+        for k in (1, 2):   # accum_pass.frag.glsl:45-53
+            mean = (mean * np.float32(k) + singles[k]) * (np.float32(1.0) / np.float32(k + 1))
+        assert np.allclose(a, mean, rtol=2e-6, atol=1e-7)
+        vis = device.read_visibility()
+        emitter = (vis >> 31 != 0) & (vis != 0xFFFFFFFF)
+        assert np.all(a[emitter][:, :3] == np.float32(1.5)) and np.all(a[..., 3] == 1.0)
+        assert np.all(np.isfinite(a))
+        images[precision] = a
+    rmse, agree = image_metrics(images["fast"], images["exact"])
+    print(f"1920x1080 fast vs exact, 3 frames: rel_rmse={rmse:.3e} agree={agree:.5f}")
+    assert agree >= 0.99

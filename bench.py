@@ -304,9 +304,11 @@ def main():
     # tear down in dependency order: the device object references the gather slab; the library's own CUDA runtime
     # instance must not outlive torch's tensors at interpreter exit
     dev.set_accum_buffer(0)
-    app.close()
-    del gat, flush, host_frame, stream, start, end
     torch.cuda.synchronize()
+    del gat, flush, host_frame, start, end
+    torch.cuda.empty_cache()
+    del stream
+    app.close()
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()

@@ -98,7 +98,7 @@ class Device:
         _check(lib().risltc_cuda_set_variant(self.h, C.byref(var)))
 
     def set_precision(self, mode):
-        _check(lib().risltc_cuda_set_precision(self.h, C.c_uint32({"fast": 0, "exact": 1}[mode])))
+        _check(lib().risltc_cuda_set_precision(self.h, C.c_uint32({"fast": 0, "exact": 1, "hybrid": 2}[mode])))
 
     def resize(self, width, height, stripe_height=8, stripe_index=0, stripe_count=1):
         _check(lib().risltc_cuda_resize(self.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(stripe_height),

@@ -15,10 +15,9 @@ CUDA_LIB = PKG / "librisltc_cuda.so"
 HOST_LIB = PKG / "librisltc_host.so"
 
 NVCC_COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off"]
-# `exact` kernel set (api.cu): IEEE arithmetic as written, no a*b+c contraction -> rounding identical to the fp32 oracle
+# IEEE arithmetic as written, no a*b+c contraction -> plain operators round identically to the fp32 oracle; the
+# candidate loop of the fused shading kernel opts out explicitly (fmaf, MUFU approximations; csrc/common.cuh)
 NVCC_EXACT = ["-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
-# `fast` kernel set (fast.cu): what a GLSL compiler is free to do -- contraction, MUFU rcp / rsqrt / sqrt, flush-to-zero
-NVCC_FAST = ["-fmad=true", "-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 
 
 def _nvcc():
@@ -36,7 +35,7 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    units = [(CSRC / "api.cu", NVCC_EXACT), (CSRC / "fast.cu", NVCC_FAST), (CSRC / "bvh_build.cpp", [])]
+    units = [(CSRC / "api.cu", NVCC_EXACT), (CSRC / "bvh_build.cpp", [])]
     deps = [u for u, _ in units] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [PKG.parent / "include" / "risltc_cuda.h"]
     if force or _stale(CUDA_LIB, deps):
         env = {**os.environ, "CC": "gcc", "CXX": "g++"}

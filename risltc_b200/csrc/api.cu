@@ -1,8 +1,8 @@
 // api.cu -- C ABI of librisltc_cuda.so (include/risltc_cuda.h) and kernel launches.
 #include "../../include/risltc_cuda.h"
 #include "kernels.cuh"
+#include "shade_fast.cuh"
 #include "bvh_build.h"
-#include "launch.h"
 #include "clip_rotation_table.inc"
 #include <cstdio>
 #include <cstring>
@@ -38,6 +38,8 @@ struct risltc_device_s {
 	float4* own_accum = nullptr;
 	uint32_t ray_slots = 0, group_slots = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
+	int sm_count = 148, trace_resident = 1;
+	int resident[2] = { 0, 0 };   // resident CTAs per SM of ris_ltc3_kernel<false / true> for the current light count
 	unsigned long long launches = 0;
 	bool timed = false;
 	// per-frame events of the last batch: 4 per frame (before (1), after (1), after (2), after (3+4))
@@ -69,14 +71,20 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
 	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
-	CU(fast::initialize(cuda_ordinal));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+	d->sm_count = prop.multiProcessorCount;
 	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
+	CU(cudaMalloc(&d->px.ticket, sizeof(unsigned int)));
+	CU(cudaMemset(d->px.ticket, 0, sizeof(unsigned int)));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	*device = d;
 	return 0;
 }
 
 static void free_targets(risltc_device_t* d) {
+	cudaFree(d->px.pick); d->px.pick = nullptr;
 	cudaFree(d->px.visibility); cudaFree(d->px.origin); cudaFree(d->px.base); cudaFree(d->px.group);
 	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum);
 	d->px.visibility = nullptr; d->px.origin = d->px.base = d->px.group = d->px.ray_a = d->px.ray_b = nullptr;
@@ -94,7 +102,7 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	cudaSetDevice(d->ordinal);
 	if (d->stream) cudaStreamSynchronize(d->stream);
 	free_targets(d); free_scene(d);
-	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters);
+	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters); cudaFree(d->px.ticket);
 	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
@@ -193,6 +201,7 @@ extern "C" int risltc_cuda_upload_lights(risltc_device_t* d, const void* records
 		CU(cudaStreamSynchronize(d->stream));   // `packed` is pageable stack-owned memory
 	}
 	d->view.lights_tri = d->lights_tri;
+	d->resident[0] = d->resident[1] = 0;
 	d->view.lights = d->lights; d->view.light_count = light_count; d->view.light_stride4 = 3 + max_vertex_count;
 	return 0;
 }
@@ -268,6 +277,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMalloc(&d->px.visibility, pixels * sizeof(uint32_t)));
 	CU(cudaMalloc(&d->px.origin, pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->px.base, pixels * sizeof(float4)));
+	CU(cudaMalloc(&d->px.pick, pixels * sizeof(uint4)));
 	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
@@ -305,10 +315,45 @@ static void unpack_constants(FrameUniforms& f, const void* block, uint32_t accum
 	f.accum_num = accum_num;
 }
 
-template <int V>
-static void launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, bool defer) {
-	if (defer) shade_kernel<V, true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
-	else shade_kernel<V, false><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+static bool deferred_rays(const Variant& v) { return v.polygon_technique != TECH_TURK && v.polygon_technique != TECH_BASELINE && v.mis_heuristic != MIS_OPTIMAL; }
+
+// Largest light table staged in shared memory (48 bytes per triangle light), keeping >= 2 CTAs per SM
+static const uint32_t kMaxSmemLights = 2048;
+
+// (2): the specialised persistent kernel of shade_fast.cuh when the variant is the default estimator on triangle
+// lights and the device is in RISLTC_PRECISION_FAST, the generic kernel otherwise.
+static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f) {
+	const Variant& v = d->variant;
+	const bool defer = deferred_rays(v);
+	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
+		&& v.mis_heuristic == MIS_OPTIMAL_CLAMPED && v.sample_count == 1u && v.light_samples == 1u && v.fast_atan == 0u
+		&& v.min_light_vertices == 3u && v.max_light_vertices == 3u && d->view.lights_tri != nullptr;
+	if (specialised) {
+		const bool smem = d->view.light_count <= kMaxSmemLights;
+		const size_t bytes = shade_fast_smem_bytes(smem ? d->view.light_count : 0u);
+		int& resident = d->resident[smem ? 1 : 0];
+		if (!resident) {
+			if (smem) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ris_ltc3_kernel<true>, 128, bytes));
+			else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ris_ltc3_kernel<false>, 128, bytes));
+			if (resident < 1) resident = 1;
+		}
+		const uint32_t tiles_x = grid.x, tile_count = grid.x * grid.y;
+		uint32_t ctas = (uint32_t) (d->sm_count * resident);
+		if (ctas > tile_count) ctas = tile_count;
+		if (smem) ris_ltc3_kernel<true><<<ctas, 128, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		else ris_ltc3_kernel<false><<<ctas, 128, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		winner_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
+		d->launches += 1;
+	}
+	else if (v.max_light_vertices == 3) {
+		if (defer) shade_kernel<3, true><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+		else shade_kernel<3, false><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+	}
+	else {
+		if (defer) shade_kernel<4, true><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+		else shade_kernel<4, false><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+	}
+	return 0;
 }
 
 extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks, uint32_t frame_count, uint32_t first_accum_num) {
@@ -317,7 +362,6 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	if (!d->nodes || !d->materials || !d->lights || !d->ltc_rgba) return fail("render_frames: scene, materials, lights and LTC tables must be uploaded first", nullptr);
 	if (!d->px.pixel_count) return fail("render_frames: call resize first", nullptr);
 	if (d->view.light_stride4 != 3 + d->variant.max_light_vertices) return fail("render_frames: light buffer stride does not match the variant's max_light_vertices", nullptr);
-	const bool defer = d->variant.polygon_technique != TECH_TURK && d->variant.polygon_technique != TECH_BASELINE && d->variant.mis_heuristic != MIS_OPTIMAL;
 	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
 	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
 	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
@@ -328,13 +372,19 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
 		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
-		if (d->precision == RISLTC_PRECISION_FAST) { fast::launch_frame(d->stream, d->view, f, d->variant, d->stripes, d->px, fe); d->launches += 3; continue; }
 		CU(cudaEventRecord(fe[0], d->stream));
 		gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
 		CU(cudaEventRecord(fe[1], d->stream));
-		if (d->variant.max_light_vertices == 3) launch_shade<3>(d, grid, f, defer); else launch_shade<4>(d, grid, f, defer);
+		if (launch_shade(d, grid, f)) return 1;
 		CU(cudaEventRecord(fe[2], d->stream));
-		resolve_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+		if (d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant)) {
+			// (3) persistent any-hit traversal over all ray slots, (4) MIS sum + accumulation
+			const uint32_t ray_count = d->px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
+			trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count);
+			resolve_kernel<true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+			d->launches += 1;
+		}
+		else resolve_kernel<false><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
 		CU(cudaEventRecord(fe[3], d->stream));
 		d->launches += 3;
 	}

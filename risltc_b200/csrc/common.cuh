@@ -4,14 +4,11 @@
 #include <stdint.h>
 #include <math.h>
 
-// Two translation units compile the same kernels: api.cu as namespace `exact` (no contraction, IEEE
-// div / sqrt: every rounding as in the C oracle) and fast.cu as namespace `fast` (RL_FAST: fused
-// multiply-adds, MUFU rsqrt / rcp, flush-to-zero). Host-visible structs are shared.
+// One translation unit, compiled WITHOUT a*b+c contraction and with IEEE division / square root
+// (risltc_b200/build.py), so that code written with plain operators rounds exactly like the C oracle.
+// Code that may round differently says so explicitly: fmaf(), approx_rsqrt(), approx_rcp(), approx_sqrt().
 #ifndef RL_NS
 #define RL_NS exact
-#endif
-#ifndef RL_FAST
-#define RL_FAST 0
 #endif
 
 #define RL_MAX_P 8            // largest MAX_POLYGON_VERTEX_COUNT (V_max 7 + 1, main.c:191-204)
@@ -80,8 +77,10 @@ struct PixelBuffers {
 	float4* group;          // [L][pixels] {carry rgb, scale}: sum of terms that need no ray, factor W (or N) of the group
 	float4* ray_a;          // [L*S*2][pixels] {dir xyz, t_max}
 	float4* ray_b;          // [L*S*2][pixels] {term rgb, valid}
+	uint4* pick;            // [pixels] RIS winner of the specialised path: light index, W (float bits), RNG state, unused
 	float4* accum;          // [pixels] RGBA32F running mean
 	unsigned long long* counters;   // [0] shaded pixels, [1] rays traced, [3] candidates
+	unsigned int* ticket;           // next unclaimed ray number of trace_kernel (zero between frames)
 	uint32_t pixel_count;
 };
 
@@ -100,11 +99,11 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return mk2(a.x - b.
 __device__ __forceinline__ float2 scale2(float2 a, float s) { return mk2(a.x * s, a.y * s); }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // GLSL inversesqrt / normalize as the oracle defines them: 1/sqrt (both correctly rounded), then multiply
-#if RL_FAST
-__device__ __forceinline__ float inversesqrt(float x) { return rsqrtf(x); }   // one MUFU.RSQ
-#else
 __device__ __forceinline__ float inversesqrt(float x) { return 1.0f / sqrtf(x); }
-#endif
+// single MUFU instructions (about 1 ulp, denormals flushed) for the paths where the rounding is free
+__device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float3 normalize3(float3 a) { return scale3(a, inversesqrt(dot3(a, a))); }
 __device__ __forceinline__ float2 normalize2(float2 a) { return scale2(a, inversesqrt(dot2(a, a))); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }

@@ -225,9 +225,110 @@ __global__ void __launch_bounds__(128) shade_kernel(SceneView s, FrameUniforms f
 	}
 }
 
+// ---------------------------------------------------------------- (3)
+// Shadow rays of the deferred variants: a persistent kernel in which every lane runs its own any-hit traversal as a
+// two-track state machine -- per loop iteration at most one inner node (both children's boxes) AND one leaf triangle,
+// taken from separate stacks, which is legal because an any-hit query may visit the tree in any order -- and takes the
+// next ray from the warp's pool once enough lanes are idle, so that lanes never wait for the longest ray of a fixed
+// group of 32. Rays are numbered slot * pixel_count + pixel; a ray record is {dir, t_max} + {term, state}: state 0 = no
+// ray, 1 = requested (visible unless proven otherwise), 2 = occluded (written here); consumed by the accumulation kernel.
+#define RL_TRACE_CHUNK 256u
+#define RL_TRACE_REFILL 6      // refill the warp when this many lanes are idle
+#define RL_LEAF_STACK 24
+
+__device__ __forceinline__ bool slab_fma(float4 lo_hi_a, float2 hi_b, float3 inv, float3 oi, float t_min, float t_max) {
+	// box {lo.xyz, hi.x} + {hi.y, hi.z}; t = plane * inv - o * inv (boxes are padded, see bvh.cuh)
+	float ax = fmaf(lo_hi_a.x, inv.x, -oi.x), bx = fmaf(lo_hi_a.w, inv.x, -oi.x);
+	float ay = fmaf(lo_hi_a.y, inv.y, -oi.y), by = fmaf(hi_b.x, inv.y, -oi.y);
+	float az = fmaf(lo_hi_a.z, inv.z, -oi.z), bz = fmaf(hi_b.y, inv.z, -oi.z);
+	float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), t_min));
+	float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_max));
+	return t0 <= t1;
+}
+
+__global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px, uint32_t ray_count) {
+	const uint32_t lane = threadIdx.x & 31u;
+	int node_stack[RL_STACK];
+	int leaf_stack[RL_LEAF_STACK];
+	uint32_t pool_next = 0, pool_end = 0;   // warp-uniform: the warp's current chunk of ray numbers
+	bool exhausted = false, busy = false;
+	uint32_t ray = 0, tri_i = 0, tri_end = 0;
+	float3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), inv = mk3(0.0f, 0.0f, 0.0f), oi = mk3(0.0f, 0.0f, 0.0f);
+	float t_max = 0.0f;
+	int node = -1, nsp = 0, lsp = 0;
+	const float t_min = 1.0e-3f;
+	while (true) {
+		const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+		if (__popc(idle) >= RL_TRACE_REFILL || (idle && exhausted)) {
+			if (pool_next >= pool_end && !exhausted) {
+				uint32_t base = 0;
+				if (lane == 0) base = atomicAdd(px.ticket, RL_TRACE_CHUNK);
+				base = __shfl_sync(0xFFFFFFFFu, base, 0);
+				pool_next = base; pool_end = min(base + RL_TRACE_CHUNK, ray_count);
+				if (base >= ray_count) { exhausted = true; pool_next = pool_end = 0u; }
+			}
+			if (exhausted && idle == 0xFFFFFFFFu) break;
+			if (!busy) {
+				const uint32_t mine = pool_next + __popc(idle & ((1u << lane) - 1u));
+				if (mine < pool_end && __ldg(&((const float*) px.ray_b)[4 * (size_t) mine + 3]) == 1.0f) {
+					const float4 ra = px.ray_a[mine], og = px.origin[mine % px.pixel_count];
+					if (t_min < ra.w) {
+						ray = mine; busy = true;
+						o = mk3(og.x, og.y, og.z); d = mk3(ra.x, ra.y, ra.z); t_max = ra.w;
+						// box tests only: an approximate reciprocal is covered by the padding of the boxes; a zero component
+						// gives inf and then inf / nan slab bounds that fminf / fmaxf ignore like the exact form does
+						inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
+						oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+						node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
+					}
+				}
+			}
+			pool_next = min(pool_next + (uint32_t) __popc(idle), pool_end);
+		}
+		if (busy) {
+			// ---- track A: one inner node
+			if (node >= 0) {
+				const BvhNode n = s.nodes[node];
+				const bool hl = slab_fma(n.a, make_float2(n.b.x, n.b.y), inv, oi, t_min, t_max);
+				const bool hr = slab_fma(make_float4(n.b.z, n.b.w, n.c.x, n.c.y), make_float2(n.c.z, n.c.w), inv, oi, t_min, t_max);
+				int next = -1;
+				#pragma unroll
+				for (int side = 0; side != 2; ++side) {
+					const int child = side ? n.d.y : n.d.x;
+					if (!(side ? hr : hl)) continue;
+					if (child >= 0) { if (next < 0) next = child; else node_stack[nsp++] = child; }
+					else if (tri_i == tri_end) { const uint32_t ref = ~(uint32_t) child; tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u; }
+					else leaf_stack[lsp++] = child;
+				}
+				node = (next >= 0) ? next : (nsp ? node_stack[--nsp] : -1);
+				// a full leaf stack pauses track A until track B has drained it (two more pushes must always fit)
+				if (lsp > RL_LEAF_STACK - 2 && node >= 0) { node_stack[nsp++] = node; node = -2; }
+			}
+			else if (node == -2 && lsp <= RL_LEAF_STACK - 2) node = node_stack[--nsp];
+			// ---- track B: one triangle
+			if (tri_i != tri_end) {
+				if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
+					((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
+					busy = false;
+				}
+				else if (++tri_i == tri_end && lsp) {
+					const uint32_t ref = ~(uint32_t) leaf_stack[--lsp];
+					tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
+				}
+			}
+			if (node == -1 && tri_i == tri_end) busy = false;   // nothing left: the ray reaches the light
+		}
+	}
+}
+
 // ------------------------------------------------------------ (3) + (4)
+// In-place variant: traces the deferred rays of its own pixel (kept for devices / variants that do not use trace_kernel);
+// with TRACED = true the rays were decided by trace_kernel and this is kernel (4) alone: MIS sum in the reference's
+// order, NaN guard, exposure (shading_pass.frag.glsl:764-769) and the running mean of accum_pass.frag.glsl:45-53.
+template <bool TRACED>
 __global__ void __launch_bounds__(128) resolve_kernel(SceneView s, FrameUniforms f, Variant var, Stripes st, PixelBuffers out) {
 	uint32_t x, row, y;
+	if (TRACED && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *out.ticket = 0u;   // next frame's ray pool
 	if (!tile_pixel(f, st, x, row, y)) return;
 	const uint32_t pixel = row * f.width + x;
 	float4 o4 = out.origin[pixel], b4 = out.base[pixel];
@@ -242,10 +343,15 @@ __global__ void __launch_bounds__(128) resolve_kernel(SceneView s, FrameUniforms
 			size_t slot = (size_t) (j * S * 2u + k) * out.pixel_count + pixel;
 			float4 rb = out.ray_b[slot];
 			if (rb.w == 0.0f) continue;
-			float4 ra = out.ray_a[slot];
 			out.ray_b[slot].w = 0.0f;   // slots are consumed: the next frame starts clean
 			++rays;
-			if (!bvh_any_hit(s, origin, mk3(ra.x, ra.y, ra.z), 1.0e-3f, ra.w)) sum = add3(sum, mk3(rb.x, rb.y, rb.z));
+			bool visible;
+			if (TRACED) visible = (rb.w == 1.0f);
+			else {
+				float4 ra = out.ray_a[slot];
+				visible = !bvh_any_hit(s, origin, mk3(ra.x, ra.y, ra.z), 1.0e-3f, ra.w);
+			}
+			if (visible) sum = add3(sum, mk3(rb.x, rb.y, rb.z));
 		}
 		sum = scale3(sum, 1.0f / (float) S);
 		sum = scale3(sum, g.w);

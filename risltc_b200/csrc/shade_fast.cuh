@@ -2,7 +2,7 @@
 // ("ours", main.c:220-236): light_reservoir with m = 32 candidates whose target function is the
 // analytic LTC integral (shading_pass.frag.glsl:723-761, :430-456) over TRIANGLE lights, winner
 // shaded by projected-solid-angle + LTC-warped samples combined with optimal-clamped MIS
-// (:292-397). Compiled only in the `fast` translation unit.
+// (:292-397). Selected by RISLTC_PRECISION_FAST (include/risltc_cuda.h).
 //
 // What differs from the generic kernel (kernels.cuh) is organisation, not the algorithm:
 //  * persistent CTAs (grid = SMs x resident CTAs) walk 16x8 pixel tiles; the light table is staged
@@ -15,7 +15,11 @@
 //  * horizon clipping of a triangle is a register-only case split (all above / all below / one or
 //    two vertices above), only the mixed cases take the slow path;
 //  * r < w / w_sum is tested as r * w_sum < w; the reservoir stays strictly sequential per pixel, so
-//    the random stream and the prefix sums keep the reference's order.
+//    the random stream and the prefix sums keep the reference's order;
+//  * the pass is split at the reservoir into ris_ltc3_kernel (G-buffer decode, LTC lookup, 32 candidates,
+//    reservoir; ~40 KB of SASS, FP32-bound) and winner_kernel (the chosen light's PSA + LTC MIS estimator,
+//    exactly rounded; ~90 KB of SASS executed once per pixel): fused, the winner's code evicted the candidate
+//    loop from the instruction cache (ncu: 7.4 warps stalled on no_instruction per issue, profiles/).
 #pragma once
 #include "kernels.cuh"
 
@@ -25,12 +29,12 @@ __device__ __forceinline__ float ff_edge(float3 a, float3 b) {   // integrateEdg
 	float x = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), y = fabsf(x);
 	float num = fmaf(fmaf(0.0145206f, y, 0.4965155f), y, 0.8543985f);
 	float den = fmaf(4.1616724f + y, y, 3.4175940f);
-	float v = __fdividef(num, den);
-	float alt = fmaf(0.5f, rsqrtf(fmaxf(fmaf(-x, x, 1.0f), 1e-7f)), -v);
+	float v = num * approx_rcp(den);
+	float alt = fmaf(0.5f, approx_rsqrt(fmaxf(fmaf(-x, x, 1.0f), 1e-7f)), -v);
 	float t = (x > 0.0f) ? v : alt;
 	return fmaf(a.x, b.y, -a.y * b.x) * t;
 }
-__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, rsqrtf(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z)))); }
+__device__ __forceinline__ float3 unit3(float3 a) { return scale3(a, approx_rsqrt(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z)))); }
 
 // Mixed horizon cases of a triangle: 1 vertex above -> triangle, 2 above -> quad (polygon_clipping.glsl:35-225
 // restricted to vertex_count == 3). Registers only.
@@ -69,86 +73,154 @@ __device__ __forceinline__ float ff_triangle(float3 p0, float3 p1, float3 p2) {
 	return result;
 }
 
-#define RL_FAST_MIN_BLOCKS 3
+#define RL_FAST_MIN_BLOCKS 4
+#define RL_CHUNK 16          // candidates per pass (two passes cover m = 32)
+#define RL_QUEUE 96          // clipped-polygon work items per warp
+#define RL_ITEM_WORDS 12     // p0, p1, p2, mask, destination slot, pad
+
+// Shared memory of one CTA (128 threads): [3 N float4 light table][2 * RL_CHUNK * 128 floats form factors]
+// [4 warps * RL_QUEUE * 12 words work items][4 queue counters]
+__host__ __device__ inline size_t shade_fast_smem_bytes(uint32_t staged_lights) {
+	return (size_t) staged_lights * 48 + 2 * RL_CHUNK * 128 * 4 + 4 * RL_QUEUE * RL_ITEM_WORDS * 4 + 16;
+}
+
+// Horizon-crossing triangles are rare per lane (a few percent) but almost every warp has one in every iteration, so
+// evaluating them in place would run the slow path with ~2 of 32 lanes active. Instead the lane parks the polygon in
+// its warp's queue and the warp later evaluates the queued polygons with all lanes busy.
+__device__ __forceinline__ void park_polygon(float* queue, int* counter, float3 p0, float3 p1, float3 p2, uint32_t mask, uint32_t dest) {
+	int slot = atomicAdd(counter, 1);
+	float4* item = (float4*) (queue + slot * RL_ITEM_WORDS);
+	item[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+	item[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+	item[2] = make_float4(p2.z, __uint_as_float(mask), __uint_as_float(dest), 0.0f);
+}
+__device__ __forceinline__ void drain_queue(const float* queue, int* counter, float* ff, uint32_t lane) {
+	__syncwarp();
+	const int count = *(volatile int*) counter;
+	for (int q = (int) lane; q < count; q += 32) {
+		const float4* item = (const float4*) (queue + q * RL_ITEM_WORDS);
+		float4 a = item[0], b = item[1], c = item[2];
+		ff[__float_as_uint(c.z)] = ff_clipped_triangle(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), __float_as_uint(c.y));
+	}
+	__syncwarp();
+	if (lane == 0) *counter = 0;
+	__syncwarp();
+}
+
+// form factor of the triangle when it is entirely above the horizon, 0 when entirely below; `partial` otherwise
+__device__ __forceinline__ float ff_triangle_or_park(float3 p0, float3 p1, float3 p2, uint32_t& mask) {
+	mask = (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
+	float result = 0.0f;
+	if (mask == 7u) {
+		float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
+		result = fabsf(ff_edge(a, b) + ff_edge(b, c) + ff_edge(c, a));
+	}
+	return result;
+}
 
 template <bool SMEM>
-__global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) shade_ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
-	extern __shared__ float4 sm_lights[];
+__global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+	extern __shared__ float4 sm_base[];
 	const int N = (int) s.light_count;
-	if (SMEM) {
-		for (uint32_t i = threadIdx.x; i < 3u * (uint32_t) N; i += blockDim.x) sm_lights[i] = __ldg(&s.lights_tri[i]);
-		__syncthreads();
-	}
-	const float4* table = SMEM ? sm_lights : s.lights_tri;
-	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t staged = SMEM ? (uint32_t) N : 0u;
+	float* sm_ff = (float*) (sm_base + 3u * staged);               // [2][RL_CHUNK][128]
+	float* sm_queue = sm_ff + 2 * RL_CHUNK * 128;                    // [4][RL_QUEUE][RL_ITEM_WORDS]
+	int* sm_count = (int*) (sm_queue + 4 * RL_QUEUE * RL_ITEM_WORDS);
+	if (SMEM) for (uint32_t i = threadIdx.x; i < 3u * staged; i += blockDim.x) sm_base[i] = __ldg(&s.lights_tri[i]);
+	if (threadIdx.x < 4) sm_count[threadIdx.x] = 0;
+	__syncthreads();
+	const float4* table = SMEM ? sm_base : s.lights_tri;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, tid = threadIdx.x;
+	float* queue = sm_queue + warp * RL_QUEUE * RL_ITEM_WORDS;
+	int* counter = sm_count + warp;
+	const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
 	uint32_t shaded = 0;
 	for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x) {
 		const uint32_t x = (tile % tiles_x) * 16u + (warp & 1u) * 8u + (lane & 7u);
 		const uint32_t row = (tile / tiles_x) * 8u + (warp >> 1) * 4u + (lane >> 3);
-		if (x >= f.width || row >= st.owned_rows) continue;
-		const uint32_t y = st.global_row(row);
-		if (y >= f.height) continue;
+		const bool inside = x < f.width && row < st.owned_rows;
+		const uint32_t y = st.global_row(inside ? row : 0u);
 		const uint32_t pixel = row * f.width + x;
-		const uint32_t prim = out.visibility[pixel];
-		if (prim == 0xFFFFFFFFu || (prim >> 31) != 0u) {
+		const uint32_t prim = (inside && y < f.height) ? out.visibility[pixel] : 0xFFFFFFFEu;
+		const bool active = prim != 0xFFFFFFFFu && (prim >> 31) == 0u;
+		if (inside && y < f.height && !active) {
 			float v = (prim == 0xFFFFFFFFu) ? 0.0f : 1.0f;
 			out.base[pixel] = make_float4(v, v, v, (prim == 0xFFFFFFFFu) ? 1.0f : 0.0f);
 			out.origin[pixel] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
-			continue;
 		}
-		++shaded;
-		ShadingPoint sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
-		float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
-		LtcFrame ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
-		uint32_t seed = noise_seed(x, y, f.width, f.frame_word);
-		// ---- RIS over 32 candidates
-		const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
+		ShadingPoint sp;
+		LtcFrame ltc;
+		uint32_t seed = 0;
+		if (active) {
+			++shaded;
+			sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
+			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+			seed = noise_seed(x, y, f.width, f.frame_word);
+		}
+		// ---- RIS over 32 candidates, RL_CHUNK at a time
 		float w_sum = 0.0f, chosen_p_hat = 0.0f;
 		int chosen = -1;
-		#pragma unroll 2
-		for (int i = 0; i != 32; ++i) {
-			seed = 1664525u * seed + 1013904223u;
-			int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
-			const float4 A = table[3 * idx], B = table[3 * idx + 1], C = table[3 * idx + 2];
-			float3 p0, p1, p2;
-			p0.x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
-			p0.y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
-			p0.z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
-			p1.x = fmaf(ltc.rx.x, B.x, fmaf(ltc.rx.y, B.y, fmaf(ltc.rx.z, B.z, ltc.t.x)));
-			p1.y = fmaf(ltc.ry.x, B.x, fmaf(ltc.ry.y, B.y, fmaf(ltc.ry.z, B.z, ltc.t.y)));
-			p1.z = fmaf(ltc.rz.x, B.x, fmaf(ltc.rz.y, B.y, fmaf(ltc.rz.z, B.z, ltc.t.z)));
-			p2.x = fmaf(ltc.rx.x, C.x, fmaf(ltc.rx.y, C.y, fmaf(ltc.rx.z, C.z, ltc.t.x)));
-			p2.y = fmaf(ltc.ry.x, C.x, fmaf(ltc.ry.y, C.y, fmaf(ltc.ry.z, C.z, ltc.t.y)));
-			p2.z = fmaf(ltc.rz.x, C.x, fmaf(ltc.rz.y, C.y, fmaf(ltc.rz.z, C.z, ltc.t.z)));
-			float fd = ff_triangle(p0, p1, p2);
-			float3 q0 = mk3(fmaf(ltc.s00, p0.x, ltc.s02 * p0.z), ltc.s11 * p0.y, fmaf(ltc.s20, p0.x, ltc.s22 * p0.z));
-			float3 q1 = mk3(fmaf(ltc.s00, p1.x, ltc.s02 * p1.z), ltc.s11 * p1.y, fmaf(ltc.s20, p1.x, ltc.s22 * p1.z));
-			float3 q2 = mk3(fmaf(ltc.s00, p2.x, ltc.s02 * p2.z), ltc.s11 * p2.y, fmaf(ltc.s20, p2.x, ltc.s22 * p2.z));
-			float fs = ff_triangle(q0, q1, q2) * ltc.albedo;
-			float cr = fmaf(sp.diffuse_albedo.x, fd, fs) * A.w, cg = fmaf(sp.diffuse_albedo.y, fd, fs) * B.w, cb = fmaf(sp.diffuse_albedo.z, fd, fs) * C.w;
-			float p_hat = sqrtf(fmaf(cr, cr, fmaf(cg, cg, cb * cb)));
-			float w = p_hat * Nf;
-			seed = 1664525u * seed + 1013904223u;
-			float r = __uint2float_rn(seed) * 2.3283064365386962890625e-10f;
-			w_sum += w;
-			if (w > 0.0f && r * w_sum < w) { chosen = idx; chosen_p_hat = p_hat; }
+		for (int chunk = 0; chunk != 32 / RL_CHUNK; ++chunk) {
+			const uint32_t chunk_seed = seed;
+			// pass 1: LTC integrals of the candidates (target function, shading_pass.frag.glsl:430-456)
+			#pragma unroll 2
+			for (int j = 0; j != RL_CHUNK; ++j) {
+				if (active) {
+					seed = 1664525u * seed + 1013904223u;
+					int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
+					seed = 1664525u * seed + 1013904223u;   // the reservoir's draw, consumed in pass 3
+					const float4 A = table[3 * idx], B = table[3 * idx + 1], C = table[3 * idx + 2];
+					float3 p0, p1, p2;
+					p0.x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
+					p0.y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
+					p0.z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
+					p1.x = fmaf(ltc.rx.x, B.x, fmaf(ltc.rx.y, B.y, fmaf(ltc.rx.z, B.z, ltc.t.x)));
+					p1.y = fmaf(ltc.ry.x, B.x, fmaf(ltc.ry.y, B.y, fmaf(ltc.ry.z, B.z, ltc.t.y)));
+					p1.z = fmaf(ltc.rz.x, B.x, fmaf(ltc.rz.y, B.y, fmaf(ltc.rz.z, B.z, ltc.t.z)));
+					p2.x = fmaf(ltc.rx.x, C.x, fmaf(ltc.rx.y, C.y, fmaf(ltc.rx.z, C.z, ltc.t.x)));
+					p2.y = fmaf(ltc.ry.x, C.x, fmaf(ltc.ry.y, C.y, fmaf(ltc.ry.z, C.z, ltc.t.y)));
+					p2.z = fmaf(ltc.rz.x, C.x, fmaf(ltc.rz.y, C.y, fmaf(ltc.rz.z, C.z, ltc.t.z)));
+					uint32_t mask;
+					const uint32_t slot_d = (uint32_t) j * 128u + tid, slot_s = (uint32_t) (RL_CHUNK + j) * 128u + tid;
+					sm_ff[slot_d] = ff_triangle_or_park(p0, p1, p2, mask);
+					if (mask != 7u && mask != 0u) park_polygon(queue, counter, p0, p1, p2, mask, slot_d);
+					float3 q0 = mk3(fmaf(ltc.s00, p0.x, ltc.s02 * p0.z), ltc.s11 * p0.y, fmaf(ltc.s20, p0.x, ltc.s22 * p0.z));
+					float3 q1 = mk3(fmaf(ltc.s00, p1.x, ltc.s02 * p1.z), ltc.s11 * p1.y, fmaf(ltc.s20, p1.x, ltc.s22 * p1.z));
+					float3 q2 = mk3(fmaf(ltc.s00, p2.x, ltc.s02 * p2.z), ltc.s11 * p2.y, fmaf(ltc.s20, p2.x, ltc.s22 * p2.z));
+					sm_ff[slot_s] = ff_triangle_or_park(q0, q1, q2, mask);
+					if (mask != 7u && mask != 0u) park_polygon(queue, counter, q0, q1, q2, mask, slot_s);
+				}
+				// at most 64 items are parked per iteration: evaluate early when the queue could overflow
+				__syncwarp();
+				if (*(volatile int*) counter > RL_QUEUE - 64) drain_queue(queue, counter, sm_ff, lane);
+			}
+			drain_queue(queue, counter, sm_ff, lane);
+			// pass 3: the reservoir in the reference's order (reservoir.glsl:34-40), replaying the chunk's draws
+			if (active) {
+				uint32_t replay = chunk_seed;
+				#pragma unroll 4
+				for (int j = 0; j != RL_CHUNK; ++j) {
+					replay = 1664525u * replay + 1013904223u;
+					int idx = min((int) (__uint2float_rn(replay) * index_scale), N - 1);
+					replay = 1664525u * replay + 1013904223u;
+					float r = __uint2float_rn(replay) * 2.3283064365386962890625e-10f;
+					const float* rec = (const float*) (table + 3 * idx);
+					float fd = sm_ff[j * 128 + tid], fs = sm_ff[(RL_CHUNK + j) * 128 + tid] * ltc.albedo;
+					float cr = fmaf(sp.diffuse_albedo.x, fd, fs) * rec[3], cg = fmaf(sp.diffuse_albedo.y, fd, fs) * rec[7], cb = fmaf(sp.diffuse_albedo.z, fd, fs) * rec[11];
+					float p_hat = approx_sqrt(fmaf(cr, cr, fmaf(cg, cg, cb * cb)));
+					float w = p_hat * Nf;
+					w_sum += w;
+					if (w > 0.0f && r * w_sum < w) { chosen = idx; chosen_p_hat = p_hat; }
+				}
+			}
+			__syncwarp();   // pass 1 of the next chunk overwrites sm_ff
 		}
-		// ---- the winner: evaluate_polygonal_light_shading_peters, rays deferred to the resolve kernel
-		float scale = 0.0f;
-		float3 carry = mk3(0.0f, 0.0f, 0.0f);
-		uint32_t rays = 0;
-		if (chosen >= 0) {
-			Light<3> light = load_light<3>(s, (uint32_t) chosen);
-			scale = (chosen_p_hat == 0.0f) ? 0.0f : w_sum / (32.0f * chosen_p_hat);
-			ShadeContext<3, true> c = { s, f, var, out, pixel, seed, 0u };
-			carry = sample_light<3, true>(c, sp, ltc, light, true, false, 0u);
-			rays = c.rays;
+		// ---- hand the winner to winner_kernel: light index, W = w_sum / (m p_hat) (shading_pass.frag.glsl:747-752), RNG state
+		if (active) {
+			float scale = (chosen < 0 || chosen_p_hat == 0.0f) ? 0.0f : w_sum / (32.0f * chosen_p_hat);
+			out.pick[pixel] = make_uint4((uint32_t) chosen, __float_as_uint(scale), seed, 0u);
 		}
-		(void) rays;
-		out.group[pixel] = make_float4(carry.x, carry.y, carry.z, scale);
-		out.base[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
 	}
 	// counters: one atomic per warp at the end of the CTA's life
 	unsigned total = __reduce_add_sync(0xFFFFFFFFu, shaded);
@@ -156,6 +228,30 @@ __global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) shade_ris_ltc3_kernel
 		atomicAdd(&out.counters[0], (unsigned long long) total);
 		atomicAdd(&out.counters[3], 32ull * total);
 	}
+}
+
+// The winner's estimator (evaluate_polygonal_light_shading_peters, shading_pass.frag.glsl:292-397) for the light that
+// ris_ltc3_kernel chose; shadow rays are deferred to the resolve kernel. Every operation here is rounded as in the oracle.
+__global__ void __launch_bounds__(128) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out) {
+	uint32_t x, row, y;
+	if (!tile_pixel(f, st, x, row, y)) return;
+	const uint32_t pixel = row * f.width + x;
+	const uint32_t prim = out.visibility[pixel];
+	if (prim == 0xFFFFFFFFu || (prim >> 31) != 0u) return;   // base / origin were written by ris_ltc3_kernel
+	const uint4 pick = out.pick[pixel];
+	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
+	ShadingPoint sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
+	float3 carry = mk3(0.0f, 0.0f, 0.0f);
+	if ((int) pick.x >= 0) {
+		float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+		LtcFrame ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+		Light<3> light = load_light<3>(s, pick.x);
+		ShadeContext<3, true> c = { s, f, var, out, pixel, pick.z, 0u };
+		carry = sample_light<3, true>(c, sp, ltc, light, true, false, 0u);
+	}
+	out.group[pixel] = make_float4(carry.x, carry.y, carry.z, __uint_as_float(pick.y));
+	out.base[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
 }
 
 }  // namespace RL_NS

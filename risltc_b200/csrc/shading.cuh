@@ -329,7 +329,7 @@ __device__ void psa_sort(PsaPolygon<P>& p) {   // :444-506
 
 // prepare_projected_solid_angle_polygon_sampling, :545-613
 template <int P>
-__device__ void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
+__device__ __noinline__ void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
 	p.vc = vc;
 	float2 inner0 = mk2(1.0f, 0.0f);
 	p.v[0] = mk2(v[0].x, v[0].y);
@@ -440,7 +440,7 @@ __device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 i
 
 // sample_projected_solid_angle_polygon, :772-828
 template <int P>
-__device__ float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
+__device__ __noinline__ float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
 	float target = u0 * p.total;
 	float2 s, outer = mk2(0.0f, 0.0f), d0 = mk2(0.0f, 0.0f);
 	if (p.inner0.x > 0.0f) {

@@ -122,8 +122,9 @@ class RefHost:
 
     def __init__(self, path=None):
         self.lib = C.CDLL(str(path or (REF_DIR / "libref_host.so")))
-        self.lib.ref_wang_random_number.restype = C.c_uint32
-        self.lib.ref_half_to_float.restype = C.c_float
+        if path is None:   # the helper exports only exist in oracle/_ref; the struct-level functions are shared names
+            self.lib.ref_wang_random_number.restype = C.c_uint32
+            self.lib.ref_half_to_float.restype = C.c_float
 
     def make_light(self, light):
         n = len(light["vertices_plane_space"])

@@ -155,3 +155,50 @@ def test_full_size_properties(device, ltc_tables):
     rmse, agree = image_metrics(images["fast"], images["exact"])
     print(f"1920x1080 fast vs exact, 3 frames: rel_rmse={rmse:.3e} agree={agree:.5f}")
     assert agree >= 0.99
+
+
+def test_host_layer_path_equals_direct_path(ltc_tables, tmp_path):
+    """The reference-shaped path (scene files -> load_scene / quick_load / load_ltc_table -> write_lights /
+    write_constants -> C ABI) renders the same image as uploading numpy arrays directly, and as the oracle."""
+    from oracle import orc
+    from risltc_b200 import api, host, scenes
+    fits, rgba, rg = ltc_tables
+    W, H = 160, 90
+    scene = scenes.many_light_room(16, 20, seed=12, width=W, height=H)
+    # load_ltc_table(dir, 51) wants 51 Fresnel layers: repeat the small table's layers
+    idx = np.minimum(np.arange(51) * rgba.shape[0] // 51, rgba.shape[0] - 1)
+    fits51 = np.asarray(fits)[idx]
+    vks, tex, save = host.write_scene_files(scene, tmp_path, ltc_fits=fits51)
+    app = host.Application(tmp_path)
+    try:
+        app.load(vks, tex, save, W, H)
+        app.settings(accum=1)
+        app.reset(0)
+        blocks = []
+        consts_before = app.write_constants()     # advances the noise seed like a rendered frame would
+        app.reset(0)
+        app.render_frames(2)
+        got = app.device().read_accum()
+        lights = np.frombuffer(app.write_lights(), dtype=np.float32).reshape(16, -1)
+    finally:
+        app.close()
+    from risltc_b200 import ltc_fit
+    rgba51, rg51 = ltc_fit.quantize_fits(fits51)
+    osc = orc.OracleScene(scene, rgba51, rg51)
+    assert np.array_equal(lights.view(np.uint32), osc.records.view(np.uint32)), "write_lights differs from the oracle's record stream"
+    cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba51.shape[1], ltc_layers=51) for f in range(2)]
+    want = bytearray(C_string(cs[0]))
+    words = orc.frame_words(0)   # set_noise_constants fills all four words; the shader reads only [0] (noise_utility.glsl:82)
+    for i in range(4):
+        want[208 + 4 * i:212 + 4 * i] = int(words[i]).to_bytes(4, "little")
+    diff = [i for i in range(256) if consts_before[i] != want[i]]
+    assert not diff, f"write_constants differs from the oracle's block at bytes {diff}"
+    ref, _, _ = osc.render(cs, orc.variant())
+    rmse, agree = image_metrics(got, ref)
+    print(f"host layer path: rel_rmse={rmse:.3e} agree={agree:.5f}")
+    assert agree >= 0.99
+
+
+def C_string(c):
+    import ctypes
+    return ctypes.string_at(ctypes.byref(c), 256)

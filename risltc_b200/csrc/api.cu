@@ -5,6 +5,7 @@
 #include "bvh_build.h"
 #include "clip_rotation_table.inc"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -128,7 +129,9 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	std::vector<float> verts;
 	dequantize_mesh_for_bvh(quantized_positions, T, factor, summand, verts);
 	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
-	build_bvh(verts.data(), T, nodes, order);
+	uint32_t max_leaf = 4;
+	if (const char* e = getenv("RISLTC_BVH_LEAF")) max_leaf = (uint32_t) atoi(e);
+	build_bvh(verts.data(), T, nodes, order, max_leaf);
 	std::vector<BvhNode> dn(nodes.size());
 	for (size_t i = 0; i != nodes.size(); ++i) {
 		const BvhNodeHost& n = nodes[i];

@@ -29,7 +29,7 @@ struct Builder {
 	std::vector<BvhNodeHost>* nodes;
 	float pad;
 	static constexpr int kBins = 16;
-	static constexpr uint32_t kLeaf = 4;
+	uint32_t kLeaf = 4;   // largest leaf
 
 	// Returns the child reference for [first, first + count) and its bounds.
 	int build(uint32_t first, uint32_t count, Box& bounds) {
@@ -115,8 +115,9 @@ void dequantize_mesh_for_bvh(const uint32_t* q, uint64_t triangle_count, const f
 	}
 }
 
-void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order) {
+void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order, uint32_t max_leaf) {
 	Builder b;
+	b.kLeaf = max_leaf < 1 ? 1 : (max_leaf > 16 ? 16 : max_leaf);
 	b.verts = verts; b.nodes = &nodes;
 	b.tri_box.resize(triangle_count); b.centroid.resize(3 * triangle_count); b.order.resize(triangle_count);
 	Box all; all.reset();

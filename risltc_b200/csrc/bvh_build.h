@@ -13,4 +13,4 @@ void dequantize_mesh_for_bvh(const uint32_t* quantized_positions, uint64_t trian
 	const float factor[3], const float summand[3], std::vector<float>& verts);
 
 // verts: 9 floats per triangle. order[slot] = triangle index stored at that leaf slot.
-void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order);
+void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order, uint32_t max_leaf = 4);

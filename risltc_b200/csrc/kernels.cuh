@@ -286,37 +286,34 @@ __global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px
 			pool_next = min(pool_next + (uint32_t) __popc(idle), pool_end);
 		}
 		if (busy) {
-			// ---- track A: one inner node
-			if (node >= 0) {
+			// ---- track A: one inner node (paused while the leaf stack could overflow: track B drains it)
+			if (node >= 0 && lsp <= RL_LEAF_STACK - 2) {
 				const BvhNode n = s.nodes[node];
 				const bool hl = slab_fma(n.a, make_float2(n.b.x, n.b.y), inv, oi, t_min, t_max);
 				const bool hr = slab_fma(make_float4(n.b.z, n.b.w, n.c.x, n.c.y), make_float2(n.c.z, n.c.w), inv, oi, t_min, t_max);
-				int next = -1;
-				#pragma unroll
-				for (int side = 0; side != 2; ++side) {
-					const int child = side ? n.d.y : n.d.x;
-					if (!(side ? hr : hl)) continue;
-					if (child >= 0) { if (next < 0) next = child; else node_stack[nsp++] = child; }
-					else if (tri_i == tri_end) { const uint32_t ref = ~(uint32_t) child; tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u; }
-					else leaf_stack[lsp++] = child;
-				}
-				node = (next >= 0) ? next : (nsp ? node_stack[--nsp] : -1);
-				// a full leaf stack pauses track A until track B has drained it (two more pushes must always fit)
-				if (lsp > RL_LEAF_STACK - 2 && node >= 0) { node_stack[nsp++] = node; node = -2; }
+				const int cl = n.d.x, cr = n.d.y;
+				const bool il = hl && cl >= 0, ir = hr && cr >= 0;
+				if (hl && cl < 0) leaf_stack[lsp++] = cl;
+				if (hr && cr < 0) leaf_stack[lsp++] = cr;
+				if (il && ir) node_stack[nsp++] = cr;
+				if (il) node = cl;
+				else if (ir) node = cr;
+				else if (nsp) node = node_stack[--nsp];
+				else node = -1;
 			}
-			else if (node == -2 && lsp <= RL_LEAF_STACK - 2) node = node_stack[--nsp];
 			// ---- track B: one triangle
+			if (tri_i == tri_end && lsp) {
+				const uint32_t ref = ~(uint32_t) leaf_stack[--lsp];
+				tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
+			}
 			if (tri_i != tri_end) {
 				if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
 					((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
 					busy = false;
 				}
-				else if (++tri_i == tri_end && lsp) {
-					const uint32_t ref = ~(uint32_t) leaf_stack[--lsp];
-					tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
-				}
+				++tri_i;
 			}
-			if (node == -1 && tri_i == tri_end) busy = false;   // nothing left: the ray reaches the light
+			else if (node < 0) busy = false;   // nothing left on either track: the ray reaches the light
 		}
 	}
 }

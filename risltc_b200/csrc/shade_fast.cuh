@@ -107,13 +107,32 @@ __device__ __forceinline__ void drain_queue(const float* queue, int* counter, fl
 	__syncwarp();
 }
 
+// integrateEdgeVec split in two: the rational fit v(|x|) that every edge needs, and the branch for x <= 0 (more than 90
+// degrees between two vertices as seen from the shading point) that few polygons need
+__device__ __forceinline__ float ff_fit(float y) {
+	float num = fmaf(fmaf(0.0145206f, y, 0.4965155f), y, 0.8543985f);
+	float den = fmaf(4.1616724f + y, y, 3.4175940f);
+	return num * approx_rcp(den);
+}
+__device__ __forceinline__ float ff_obtuse(float x, float v) { return fmaf(0.5f, approx_rsqrt(fmaxf(fmaf(-x, x, 1.0f), 1e-7f)), -v); }
+
 // form factor of the triangle when it is entirely above the horizon, 0 when entirely below; `partial` otherwise
 __device__ __forceinline__ float ff_triangle_or_park(float3 p0, float3 p1, float3 p2, uint32_t& mask) {
 	mask = (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
 	float result = 0.0f;
 	if (mask == 7u) {
 		float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
-		result = fabsf(ff_edge(a, b) + ff_edge(b, c) + ff_edge(c, a));
+		float xab = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), xbc = fmaf(b.x, c.x, fmaf(b.y, c.y, b.z * c.z)), xca = fmaf(c.x, a.x, fmaf(c.y, a.y, c.z * a.z));
+		float tab = ff_fit(fabsf(xab)), tbc = ff_fit(fabsf(xbc)), tca = ff_fit(fabsf(xca));
+		if (fminf(xab, fminf(xbc, xca)) <= 0.0f) {
+			tab = (xab > 0.0f) ? tab : ff_obtuse(xab, tab);
+			tbc = (xbc > 0.0f) ? tbc : ff_obtuse(xbc, tbc);
+			tca = (xca > 0.0f) ? tca : ff_obtuse(xca, tca);
+		}
+		float sum = fmaf(a.x, b.y, -a.y * b.x) * tab;
+		sum = fmaf(fmaf(b.x, c.y, -b.y * c.x), tbc, sum);
+		sum = fmaf(fmaf(c.x, a.y, -c.y * a.x), tca, sum);
+		result = fabsf(sum);
 	}
 	return result;
 }

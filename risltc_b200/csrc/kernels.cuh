@@ -230,10 +230,11 @@ __global__ void __launch_bounds__(128) shade_kernel(SceneView s, FrameUniforms f
 // two-track state machine -- per loop iteration at most one inner node (both children's boxes) AND one leaf triangle,
 // taken from separate stacks, which is legal because an any-hit query may visit the tree in any order -- and takes the
 // next ray from the warp's pool once enough lanes are idle, so that lanes never wait for the longest ray of a fixed
-// group of 32. Rays are numbered slot * pixel_count + pixel; a ray record is {dir, t_max} + {term, state}: state 0 = no
+// group of 32; ray records are loaded 64 at a time, coalesced, into a per-warp stage in shared memory, the following
+// 64 being prefetched into L2. Rays are numbered slot * pixel_count + pixel; a ray record is {dir, t_max} + {term, state}: state 0 = no
 // ray, 1 = requested (visible unless proven otherwise), 2 = occluded (written here); consumed by the accumulation kernel.
-#define RL_TRACE_CHUNK 256u
-#define RL_TRACE_REFILL 6      // refill the warp when this many lanes are idle
+#define RL_TRACE_STAGE 64u     // rays staged per warp in shared memory (two per lane, loaded coalesced)
+#define RL_TRACE_REFILL 6      // hand out staged rays when this many lanes are idle
 #define RL_LEAF_STACK 24
 
 __device__ __forceinline__ bool slab_fma(float4 lo_hi_a, float2 hi_b, float3 inv, float3 oi, float t_min, float t_max) {
@@ -246,44 +247,72 @@ __device__ __forceinline__ bool slab_fma(float4 lo_hi_a, float2 hi_b, float3 inv
 	return t0 <= t1;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px, uint32_t ray_count) {
-	const uint32_t lane = threadIdx.x & 31u;
+	// per warp: RL_TRACE_STAGE compacted rays as {origin, t_max}, {direction, ray number}
+	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	float4 (*stage)[2] = sm_stage[warp];
 	int node_stack[RL_STACK];
 	int leaf_stack[RL_LEAF_STACK];
-	uint32_t pool_next = 0, pool_end = 0;   // warp-uniform: the warp's current chunk of ray numbers
+	uint32_t stage_next = 0, stage_count = 0;   // warp-uniform
 	bool exhausted = false, busy = false;
 	uint32_t ray = 0, tri_i = 0, tri_end = 0;
 	float3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), inv = mk3(0.0f, 0.0f, 0.0f), oi = mk3(0.0f, 0.0f, 0.0f);
 	float t_max = 0.0f;
 	int node = -1, nsp = 0, lsp = 0;
 	const float t_min = 1.0e-3f;
+	// the chunk of ray numbers this warp will stage next: claimed one stage ahead so that its records can be pulled into L2
+	uint32_t ahead = 0;
+	if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
+	ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
 	while (true) {
 		const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
 		if (__popc(idle) >= RL_TRACE_REFILL || (idle && exhausted)) {
-			if (pool_next >= pool_end && !exhausted) {
-				uint32_t base = 0;
-				if (lane == 0) base = atomicAdd(px.ticket, RL_TRACE_CHUNK);
-				base = __shfl_sync(0xFFFFFFFFu, base, 0);
-				pool_next = base; pool_end = min(base + RL_TRACE_CHUNK, ray_count);
-				if (base >= ray_count) { exhausted = true; pool_next = pool_end = 0u; }
-			}
-			if (exhausted && idle == 0xFFFFFFFFu) break;
-			if (!busy) {
-				const uint32_t mine = pool_next + __popc(idle & ((1u << lane) - 1u));
-				if (mine < pool_end && __ldg(&((const float*) px.ray_b)[4 * (size_t) mine + 3]) == 1.0f) {
-					const float4 ra = px.ray_a[mine], og = px.origin[mine % px.pixel_count];
-					if (t_min < ra.w) {
-						ray = mine; busy = true;
-						o = mk3(og.x, og.y, og.z); d = mk3(ra.x, ra.y, ra.z); t_max = ra.w;
-						// box tests only: an approximate reciprocal is covered by the padding of the boxes; a zero component
-						// gives inf and then inf / nan slab bounds that fminf / fmaxf ignore like the exact form does
-						inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
-						oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-						node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
+			while (stage_next >= stage_count && !exhausted) {
+				// stage the chunk claimed earlier (coalesced: lane l takes rays base + l and base + l + 32) and claim the next one
+				const uint32_t base = ahead;
+				if (base >= ray_count) { exhausted = true; break; }
+				if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
+				ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
+				if (ahead + lane * 2u < ray_count) {
+					prefetch_l2(&px.ray_a[ahead + lane * 2u]); prefetch_l2(&px.ray_b[ahead + lane * 2u]);
+					prefetch_l2(&px.origin[(ahead + lane * 2u) % px.pixel_count]);
+				}
+				stage_next = stage_count = 0u;
+				#pragma unroll
+				for (uint32_t half = 0; half != 2u; ++half) {
+					const uint32_t r = base + half * 32u + lane;
+					bool valid = r < ray_count && __ldg(&((const float*) px.ray_b)[4 * (size_t) r + 3]) == 1.0f;
+					float4 ra = make_float4(0.0f, 0.0f, 1.0f, 0.0f), og = ra;
+					if (valid) { ra = px.ray_a[r]; og = px.origin[r % px.pixel_count]; valid = t_min < ra.w; }
+					const unsigned have = __ballot_sync(0xFFFFFFFFu, valid);
+					if (valid) {
+						const uint32_t slot = stage_count + __popc(have & ((1u << lane) - 1u));
+						stage[slot][0] = make_float4(og.x, og.y, og.z, ra.w);
+						stage[slot][1] = make_float4(ra.x, ra.y, ra.z, __uint_as_float(r));
 					}
+					stage_count += (uint32_t) __popc(have);
+				}
+				__syncwarp();
+			}
+			if (exhausted && stage_next >= stage_count && idle == 0xFFFFFFFFu) break;
+			if (!busy) {
+				const uint32_t mine = stage_next + __popc(idle & ((1u << lane) - 1u));
+				if (mine < stage_count) {
+					const float4 a0 = stage[mine][0], a1 = stage[mine][1];
+					ray = __float_as_uint(a1.w); busy = true;
+					o = mk3(a0.x, a0.y, a0.z); d = mk3(a1.x, a1.y, a1.z); t_max = a0.w;
+					// box tests only: an approximate reciprocal is covered by the padding of the boxes; a zero component
+					// gives inf and then inf / nan slab bounds that fminf / fmaxf ignore like the exact form does
+					inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
+					oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+					node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
 				}
 			}
-			pool_next = min(pool_next + (uint32_t) __popc(idle), pool_end);
+			stage_next = min(stage_next + (uint32_t) __popc(idle), stage_count);
+			__syncwarp();   // all reads of the stage are done before a later iteration restages
 		}
 		if (busy) {
 			// ---- track A: one inner node (paused while the leaf stack could overflow: track B drains it)

@@ -40,7 +40,7 @@ struct risltc_device_s {
 	uint32_t ray_slots = 0, group_slots = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1;
-	int resident[2] = { 0, 0 };   // resident CTAs per SM of ris_ltc3_kernel<false / true> for the current light count
+	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
 	bool timed = false;
 	// per-frame events of the last batch: 4 per frame (before (1), after (1), after (2), after (3+4))
@@ -72,14 +72,15 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
 	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
-	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	d->sm_count = prop.multiProcessorCount;
 	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
 	CU(cudaMalloc(&d->px.ticket, sizeof(unsigned int)));
 	CU(cudaMemset(d->px.ticket, 0, sizeof(unsigned int)));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
+	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knob
 	*device = d;
 	return 0;
 }
@@ -204,7 +205,6 @@ extern "C" int risltc_cuda_upload_lights(risltc_device_t* d, const void* records
 		CU(cudaStreamSynchronize(d->stream));   // `packed` is pageable stack-owned memory
 	}
 	d->view.lights_tri = d->lights_tri;
-	d->resident[0] = d->resident[1] = 0;
 	d->view.lights = d->lights; d->view.light_count = light_count; d->view.light_stride4 = 3 + max_vertex_count;
 	return 0;
 }
@@ -333,18 +333,15 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f) {
 		&& v.min_light_vertices == 3u && v.max_light_vertices == 3u && d->view.lights_tri != nullptr;
 	if (specialised) {
 		const bool smem = d->view.light_count <= kMaxSmemLights;
-		const size_t bytes = shade_fast_smem_bytes(smem ? d->view.light_count : 0u);
-		int& resident = d->resident[smem ? 1 : 0];
-		if (!resident) {
-			if (smem) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ris_ltc3_kernel<true>, 128, bytes));
-			else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ris_ltc3_kernel<false>, 128, bytes));
-			if (resident < 1) resident = 1;
-		}
-		const uint32_t tiles_x = grid.x, tile_count = grid.x * grid.y;
-		uint32_t ctas = (uint32_t) (d->sm_count * resident);
-		if (ctas > tile_count) ctas = tile_count;
-		if (smem) ris_ltc3_kernel<true><<<ctas, 128, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
-		else ris_ltc3_kernel<false><<<ctas, 128, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		const uint32_t staged = smem ? d->view.light_count : 0u;
+		const uint32_t warps = shade_fast_warps(staged);
+		const size_t bytes = shade_fast_smem_bytes(staged, warps);
+		// a warp owns 8x4 pixel tiles; one persistent CTA per SM
+		const uint32_t tiles_x = (d->width + 7) / 8, tile_count = tiles_x * ((d->stripes.owned_rows + 3) / 4);
+		uint32_t ctas = (uint32_t) d->sm_count;
+		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
+		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
 		winner_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
 		d->launches += 1;
 	}
@@ -383,7 +380,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant)) {
 			// (3) persistent any-hit traversal over all ray slots, (4) MIS sum + accumulation
 			const uint32_t ray_count = d->px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count);
+			trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
 			resolve_kernel<true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
 			d->launches += 1;
 		}

@@ -249,7 +249,7 @@ __device__ __forceinline__ bool slab_fma(float4 lo_hi_a, float2 hi_b, float3 inv
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
-__global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px, uint32_t ray_count) {
+__global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote) {
 	// per warp: RL_TRACE_STAGE compacted rays as {origin, t_max}, {direction, ray number}
 	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -314,36 +314,41 @@ __global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px
 			stage_next = min(stage_next + (uint32_t) __popc(idle), stage_count);
 			__syncwarp();   // all reads of the stage are done before a later iteration restages
 		}
-		if (busy) {
-			// ---- track A: one inner node (paused while the leaf stack could overflow: track B drains it)
-			if (node >= 0 && lsp <= RL_LEAF_STACK - 2) {
-				const BvhNode n = s.nodes[node];
-				const bool hl = slab_fma(n.a, make_float2(n.b.x, n.b.y), inv, oi, t_min, t_max);
-				const bool hr = slab_fma(make_float4(n.b.z, n.b.w, n.c.x, n.c.y), make_float2(n.c.z, n.c.w), inv, oi, t_min, t_max);
-				const int cl = n.d.x, cr = n.d.y;
-				const bool il = hl && cl >= 0, ir = hr && cr >= 0;
-				if (hl && cl < 0) leaf_stack[lsp++] = cl;
-				if (hr && cr < 0) leaf_stack[lsp++] = cr;
-				if (il && ir) node_stack[nsp++] = cr;
-				if (il) node = cl;
-				else if (ir) node = cr;
-				else if (nsp) node = node_stack[--nsp];
-				else node = -1;
-			}
-			// ---- track B: one triangle
-			if (tri_i == tri_end && lsp) {
+		// ---- votes: the inner-node track runs for every lane that has a node; the triangle track only once enough lanes
+		// have a triangle waiting (or nobody can make progress on nodes), so that its ~85 instructions run on a well
+		// filled warp instead of on the ~10 lanes that happen to have reached a leaf in this iteration
+		const bool node_ready = busy && node >= 0 && lsp <= RL_LEAF_STACK - 2;
+		const bool tri_pending = busy && (tri_i != tri_end || lsp != 0);
+		const unsigned node_votes = __ballot_sync(0xFFFFFFFFu, node_ready), tri_votes = __ballot_sync(0xFFFFFFFFu, tri_pending);
+		const bool run_tri = (uint32_t) __popc(tri_votes) >= tri_vote || node_votes == 0u;
+		// ---- track A: one inner node (paused while the leaf stack could overflow: track B drains it)
+		if (node_ready) {
+			const BvhNode n = s.nodes[node];
+			const bool hl = slab_fma(n.a, make_float2(n.b.x, n.b.y), inv, oi, t_min, t_max);
+			const bool hr = slab_fma(make_float4(n.b.z, n.b.w, n.c.x, n.c.y), make_float2(n.c.z, n.c.w), inv, oi, t_min, t_max);
+			const int cl = n.d.x, cr = n.d.y;
+			const bool il = hl && cl >= 0, ir = hr && cr >= 0;
+			if (hl && cl < 0) leaf_stack[lsp++] = cl;
+			if (hr && cr < 0) leaf_stack[lsp++] = cr;
+			if (il && ir) node_stack[nsp++] = cr;
+			if (il) node = cl;
+			else if (ir) node = cr;
+			else if (nsp) node = node_stack[--nsp];
+			else node = -1;
+		}
+		// ---- track B: one triangle
+		if (run_tri && tri_pending) {
+			if (tri_i == tri_end) {
 				const uint32_t ref = ~(uint32_t) leaf_stack[--lsp];
 				tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
 			}
-			if (tri_i != tri_end) {
-				if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
-					((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
-					busy = false;
-				}
-				++tri_i;
+			if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
+				((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
+				busy = false;
 			}
-			else if (node < 0) busy = false;   // nothing left on either track: the ray reaches the light
+			++tri_i;
 		}
+		if (busy && node < 0 && tri_i == tri_end && lsp == 0) busy = false;   // nothing left on either track: the ray reaches the light
 	}
 }
 

@@ -5,19 +5,19 @@
 // (:292-397). Selected by RISLTC_PRECISION_FAST (include/risltc_cuda.h).
 //
 // What differs from the generic kernel (kernels.cuh) is organisation, not the algorithm:
-//  * persistent CTAs (grid = SMs x resident CTAs) walk 16x8 pixel tiles; the light table is staged
-//    ONCE per CTA into shared memory as 48-byte records {v0 | Le.r, v1 | Le.g, v2 | Le.b} and the
-//    32 random candidates of every pixel are gathered from there with three LDS.128;
+//  * ONE persistent CTA per SM (up to 24 warps); the light table is staged once per CTA into shared memory as
+//    48-byte records {v0 | Le.r, v1 | Le.g, v2 | Le.b} and the 32 random candidates of every pixel are gathered from
+//    there with three LDS.128; a warp owns 8x4 pixel tiles;
 //  * the candidate needs no plane equation: flipping the shading frame's y row mirrors the polygon,
 //    which negates the signed edge sum exactly and calculate_ltc takes abs() (polygon_sampling.glsl:529);
 //  * cosine-space vertices come from the shading-space ones through the 5 non-zeros of
 //    shading_to_cosine_space instead of a second 4x3 transform of the world-space vertices;
-//  * horizon clipping of a triangle is a register-only case split (all above / all below / one or
-//    two vertices above), only the mixed cases take the slow path;
+//  * a lane only transforms and classifies its pixel's candidates; the polygons are queued per warp in shared
+//    memory and evaluated 32 at a time with all lanes busy (see "work redistribution" below);
 //  * r < w / w_sum is tested as r * w_sum < w; the reservoir stays strictly sequential per pixel, so
 //    the random stream and the prefix sums keep the reference's order;
 //  * the pass is split at the reservoir into ris_ltc3_kernel (G-buffer decode, LTC lookup, 32 candidates,
-//    reservoir; ~40 KB of SASS, FP32-bound) and winner_kernel (the chosen light's PSA + LTC MIS estimator,
+//    reservoir; FP32-bound) and winner_kernel (the chosen light's PSA + LTC MIS estimator,
 //    exactly rounded; ~90 KB of SASS executed once per pixel): fused, the winner's code evicted the candidate
 //    loop from the instruction cache (ncu: 7.4 warps stalled on no_instruction per issue, profiles/).
 #pragma once
@@ -61,50 +61,30 @@ __device__ __noinline__ float ff_clipped_triangle(float3 p0, float3 p1, float3 p
 	return fabsf(sum);
 }
 
-// |calculate_ltc| of a triangle clipped to z >= 0
-__device__ __forceinline__ float ff_triangle(float3 p0, float3 p1, float3 p2) {
-	uint32_t mask = (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
-	float result = 0.0f;
-	if (mask == 7u) {
-		float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
-		result = fabsf(ff_edge(a, b) + ff_edge(b, c) + ff_edge(c, a));
-	}
-	else if (mask != 0u) result = ff_clipped_triangle(p0, p1, p2, mask);
-	return result;
-}
+// ---- work redistribution inside a warp
+// A lane owns a pixel, but only ~half of its candidate polygons lie entirely above the horizon (the expensive, common
+// case), ~10 % cross it (the very expensive case) and the rest are below it (free). Evaluated in place, the expensive
+// code would run with 17 of 32 lanes busy (ncu, profiles/r1_ncu_shade_kernels.txt). Instead every lane only transforms
+// and classifies its candidate and PUSHES the polygon into its warp's queue in shared memory -- polygons above the
+// horizon from the bottom, horizon-crossing polygons from the top -- and whenever 32 of a kind are waiting the warp
+// evaluates them, one per lane, with all lanes busy. Slots are assigned with ballots (no atomics; the counts live in
+// warp-uniform registers). Results go to the warp's form-factor table, from which the pixel's lane replays its
+// reservoir in the reference's order.
+#define RL_CHUNK 8            // candidates per pass (four passes cover m = 32)
+#define RL_QUEUE 128          // polygons per warp queue: <= 31 + 31 left waiting + <= 64 pushed per candidate
+#define RL_ITEM_WORDS 12      // p0, p1, p2, mask, destination slot, pad: three 16-byte accesses, conflict-free at this stride
+#define RL_WARP_WORDS (2 * RL_CHUNK * 32 + RL_QUEUE * RL_ITEM_WORDS)   // 8 KB per warp
+#define RL_FAST_MAX_WARPS 24
+#define RL_SMEM_LIMIT (227u * 1024u)
 
-#define RL_FAST_MIN_BLOCKS 4
-#define RL_CHUNK 16          // candidates per pass (two passes cover m = 32)
-#define RL_QUEUE 96          // clipped-polygon work items per warp
-#define RL_ITEM_WORDS 12     // p0, p1, p2, mask, destination slot, pad
-
-// Shared memory of one CTA (128 threads): [3 N float4 light table][2 * RL_CHUNK * 128 floats form factors]
-// [4 warps * RL_QUEUE * 12 words work items][4 queue counters]
-__host__ __device__ inline size_t shade_fast_smem_bytes(uint32_t staged_lights) {
-	return (size_t) staged_lights * 48 + 2 * RL_CHUNK * 128 * 4 + 4 * RL_QUEUE * RL_ITEM_WORDS * 4 + 16;
+// Shared memory of the CTA (one per SM): [3 N float4 light table][warps x {2 * RL_CHUNK * 32 form factors, RL_QUEUE work items}]
+__host__ __device__ inline size_t shade_fast_smem_bytes(uint32_t staged_lights, uint32_t warps) {
+	return (size_t) staged_lights * 48 + (size_t) warps * RL_WARP_WORDS * 4;
 }
-
-// Horizon-crossing triangles are rare per lane (a few percent) but almost every warp has one in every iteration, so
-// evaluating them in place would run the slow path with ~2 of 32 lanes active. Instead the lane parks the polygon in
-// its warp's queue and the warp later evaluates the queued polygons with all lanes busy.
-__device__ __forceinline__ void park_polygon(float* queue, int* counter, float3 p0, float3 p1, float3 p2, uint32_t mask, uint32_t dest) {
-	int slot = atomicAdd(counter, 1);
-	float4* item = (float4*) (queue + slot * RL_ITEM_WORDS);
-	item[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
-	item[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
-	item[2] = make_float4(p2.z, __uint_as_float(mask), __uint_as_float(dest), 0.0f);
-}
-__device__ __forceinline__ void drain_queue(const float* queue, int* counter, float* ff, uint32_t lane) {
-	__syncwarp();
-	const int count = *(volatile int*) counter;
-	for (int q = (int) lane; q < count; q += 32) {
-		const float4* item = (const float4*) (queue + q * RL_ITEM_WORDS);
-		float4 a = item[0], b = item[1], c = item[2];
-		ff[__float_as_uint(c.z)] = ff_clipped_triangle(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), __float_as_uint(c.y));
-	}
-	__syncwarp();
-	if (lane == 0) *counter = 0;
-	__syncwarp();
+// Largest number of warps whose shared memory fits beside the light table
+__host__ inline uint32_t shade_fast_warps(uint32_t staged_lights) {
+	uint32_t warps = (RL_SMEM_LIMIT - staged_lights * 48u) / (RL_WARP_WORDS * 4u);
+	return warps > RL_FAST_MAX_WARPS ? RL_FAST_MAX_WARPS : warps;
 }
 
 // integrateEdgeVec split in two: the rational fit v(|x|) that every edge needs, and the branch for x <= 0 (more than 90
@@ -116,47 +96,76 @@ __device__ __forceinline__ float ff_fit(float y) {
 }
 __device__ __forceinline__ float ff_obtuse(float x, float v) { return fmaf(0.5f, approx_rsqrt(fmaxf(fmaf(-x, x, 1.0f), 1e-7f)), -v); }
 
-// form factor of the triangle when it is entirely above the horizon, 0 when entirely below; `partial` otherwise
-__device__ __forceinline__ float ff_triangle_or_park(float3 p0, float3 p1, float3 p2, uint32_t& mask) {
-	mask = (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
-	float result = 0.0f;
-	if (mask == 7u) {
-		float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
-		float xab = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), xbc = fmaf(b.x, c.x, fmaf(b.y, c.y, b.z * c.z)), xca = fmaf(c.x, a.x, fmaf(c.y, a.y, c.z * a.z));
-		float tab = ff_fit(fabsf(xab)), tbc = ff_fit(fabsf(xbc)), tca = ff_fit(fabsf(xca));
-		if (fminf(xab, fminf(xbc, xca)) <= 0.0f) {
-			tab = (xab > 0.0f) ? tab : ff_obtuse(xab, tab);
-			tbc = (xbc > 0.0f) ? tbc : ff_obtuse(xbc, tbc);
-			tca = (xca > 0.0f) ? tca : ff_obtuse(xca, tca);
-		}
-		float sum = fmaf(a.x, b.y, -a.y * b.x) * tab;
-		sum = fmaf(fmaf(b.x, c.y, -b.y * c.x), tbc, sum);
-		sum = fmaf(fmaf(c.x, a.y, -c.y * a.x), tca, sum);
-		result = fabsf(sum);
+// |calculate_ltc| of a triangle that lies entirely above the horizon
+__device__ __forceinline__ float ff_above(float3 p0, float3 p1, float3 p2) {
+	float3 a = unit3(p0), b = unit3(p1), c = unit3(p2);
+	float xab = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), xbc = fmaf(b.x, c.x, fmaf(b.y, c.y, b.z * c.z)), xca = fmaf(c.x, a.x, fmaf(c.y, a.y, c.z * a.z));
+	float tab = ff_fit(fabsf(xab)), tbc = ff_fit(fabsf(xbc)), tca = ff_fit(fabsf(xca));
+	if (fminf(xab, fminf(xbc, xca)) <= 0.0f) {
+		tab = (xab > 0.0f) ? tab : ff_obtuse(xab, tab);
+		tbc = (xbc > 0.0f) ? tbc : ff_obtuse(xbc, tbc);
+		tca = (xca > 0.0f) ? tca : ff_obtuse(xca, tca);
 	}
-	return result;
+	float sum = fmaf(a.x, b.y, -a.y * b.x) * tab;
+	sum = fmaf(fmaf(b.x, c.y, -b.y * c.x), tbc, sum);
+	sum = fmaf(fmaf(c.x, a.y, -c.y * a.x), tca, sum);
+	return fabsf(sum);
+}
+
+__device__ __forceinline__ uint32_t horizon_mask(float3 p0, float3 p1, float3 p2) {
+	return (p0.z > 0.0f ? 1u : 0u) | (p1.z > 0.0f ? 2u : 0u) | (p2.z > 0.0f ? 4u : 0u);
+}
+
+// Push one polygon of this lane: above the horizon -> bottom of the queue, crossing -> top. Polygons below the horizon
+// (and those of inactive lanes, whose z are 0) are not queued: their form factor stays at the 0 the table was cleared to.
+__device__ __forceinline__ void push_polygon(float* queue, uint32_t& count_above, uint32_t& count_crossing, uint32_t lt_mask,
+	float3 p0, float3 p1, float3 p2, uint32_t dest)
+{
+	const bool above = fminf(fminf(p0.z, p1.z), p2.z) > 0.0f, crossing = !above && fmaxf(fmaxf(p0.z, p1.z), p2.z) > 0.0f;
+	const unsigned ballot_above = __ballot_sync(0xFFFFFFFFu, above), ballot_crossing = __ballot_sync(0xFFFFFFFFu, crossing);
+	if (above || crossing) {
+		const uint32_t rank = __popc((above ? ballot_above : ballot_crossing) & lt_mask);
+		const uint32_t slot = above ? count_above + rank : (RL_QUEUE - 1u) - count_crossing - rank;
+		float4* item = (float4*) (queue + slot * RL_ITEM_WORDS);
+		item[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+		item[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+		item[2] = make_float4(p2.z, __uint_as_float(dest), 0.0f, 0.0f);
+	}
+	count_above += __popc(ballot_above);
+	count_crossing += __popc(ballot_crossing);
+}
+// Evaluate `n` (<= 32) queued polygons starting at queue slot `first`, one per lane
+template <bool ABOVE>
+__device__ __forceinline__ void drain(const float* queue, float* ff, uint32_t first, uint32_t n, uint32_t lane) {
+	__syncwarp();
+	if (lane < n) {
+		const float4* item = (const float4*) (queue + (first + lane) * RL_ITEM_WORDS);
+		const float4 a = item[0], b = item[1];
+		const float2 c = *(const float2*) (item + 2);
+		const float3 p0 = mk3(a.x, a.y, a.z), p1 = mk3(a.w, b.x, b.y), p2 = mk3(b.z, b.w, c.x);
+		ff[__float_as_uint(c.y)] = ABOVE ? ff_above(p0, p1, p2) : ff_clipped_triangle(p0, p1, p2, horizon_mask(p0, p1, p2));
+	}
+	__syncwarp();
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+__global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
 	extern __shared__ float4 sm_base[];
 	const int N = (int) s.light_count;
 	const uint32_t staged = SMEM ? (uint32_t) N : 0u;
-	float* sm_ff = (float*) (sm_base + 3u * staged);               // [2][RL_CHUNK][128]
-	float* sm_queue = sm_ff + 2 * RL_CHUNK * 128;                    // [4][RL_QUEUE][RL_ITEM_WORDS]
-	int* sm_count = (int*) (sm_queue + 4 * RL_QUEUE * RL_ITEM_WORDS);
 	if (SMEM) for (uint32_t i = threadIdx.x; i < 3u * staged; i += blockDim.x) sm_base[i] = __ldg(&s.lights_tri[i]);
-	if (threadIdx.x < 4) sm_count[threadIdx.x] = 0;
 	__syncthreads();
 	const float4* table = SMEM ? sm_base : s.lights_tri;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, tid = threadIdx.x;
-	float* queue = sm_queue + warp * RL_QUEUE * RL_ITEM_WORDS;
-	int* counter = sm_count + warp;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	float* ff = (float*) (sm_base + 3u * staged) + warp * RL_WARP_WORDS;   // [2][RL_CHUNK][32]
+	float* queue = ff + 2 * RL_CHUNK * 32;                                   // [RL_QUEUE][RL_ITEM_WORDS]
 	const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
 	uint32_t shaded = 0;
-	for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x) {
-		const uint32_t x = (tile % tiles_x) * 16u + (warp & 1u) * 8u + (lane & 7u);
-		const uint32_t row = (tile / tiles_x) * 8u + (warp >> 1) * 4u + (lane >> 3);
+	// a warp owns 8x4 pixel tiles; the warps of a CTA take neighbouring tiles
+	for (uint32_t tile = blockIdx.x * warps + warp; tile < tile_count; tile += gridDim.x * warps) {
+		const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u);
+		const uint32_t row = (tile / tiles_x) * 4u + (lane >> 3);
 		const bool inside = x < f.width && row < st.owned_rows;
 		const uint32_t y = st.global_row(inside ? row : 0u);
 		const uint32_t pixel = row * f.width + x;
@@ -167,8 +176,11 @@ __global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(Scene
 			out.base[pixel] = make_float4(v, v, v, (prim == 0xFFFFFFFFu) ? 1.0f : 0.0f);
 			out.origin[pixel] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
 		}
+		if (!__any_sync(0xFFFFFFFFu, active)) continue;
 		ShadingPoint sp;
 		LtcFrame ltc;
+		ltc.rx = ltc.ry = ltc.rz = ltc.t = mk3(0.0f, 0.0f, 0.0f);
+		ltc.s00 = ltc.s02 = ltc.s11 = ltc.s20 = ltc.s22 = 0.0f;
 		uint32_t seed = 0;
 		if (active) {
 			++shaded;
@@ -182,40 +194,43 @@ __global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(Scene
 		int chosen = -1;
 		for (int chunk = 0; chunk != 32 / RL_CHUNK; ++chunk) {
 			const uint32_t chunk_seed = seed;
-			// pass 1: LTC integrals of the candidates (target function, shading_pass.frag.glsl:430-456)
-			#pragma unroll 2
+			uint32_t count_above = 0, count_crossing = 0;   // warp-uniform
+			uint32_t dest = lane;
+			// clear the form-factor table: polygons below the horizon are never written
+			#pragma unroll
+			for (int i = 0; i != 2 * RL_CHUNK / 4; ++i) ((float4*) ff)[i * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			__syncwarp();
+			// pass 1: transform and classify the candidates (target function: LTC integrals, shading_pass.frag.glsl:430-456)
+			#pragma unroll 1
 			for (int j = 0; j != RL_CHUNK; ++j) {
-				if (active) {
-					seed = 1664525u * seed + 1013904223u;
-					int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
-					seed = 1664525u * seed + 1013904223u;   // the reservoir's draw, consumed in pass 3
-					const float4 A = table[3 * idx], B = table[3 * idx + 1], C = table[3 * idx + 2];
-					float3 p0, p1, p2;
-					p0.x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
-					p0.y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
-					p0.z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
-					p1.x = fmaf(ltc.rx.x, B.x, fmaf(ltc.rx.y, B.y, fmaf(ltc.rx.z, B.z, ltc.t.x)));
-					p1.y = fmaf(ltc.ry.x, B.x, fmaf(ltc.ry.y, B.y, fmaf(ltc.ry.z, B.z, ltc.t.y)));
-					p1.z = fmaf(ltc.rz.x, B.x, fmaf(ltc.rz.y, B.y, fmaf(ltc.rz.z, B.z, ltc.t.z)));
-					p2.x = fmaf(ltc.rx.x, C.x, fmaf(ltc.rx.y, C.y, fmaf(ltc.rx.z, C.z, ltc.t.x)));
-					p2.y = fmaf(ltc.ry.x, C.x, fmaf(ltc.ry.y, C.y, fmaf(ltc.ry.z, C.z, ltc.t.y)));
-					p2.z = fmaf(ltc.rz.x, C.x, fmaf(ltc.rz.y, C.y, fmaf(ltc.rz.z, C.z, ltc.t.z)));
-					uint32_t mask;
-					const uint32_t slot_d = (uint32_t) j * 128u + tid, slot_s = (uint32_t) (RL_CHUNK + j) * 128u + tid;
-					sm_ff[slot_d] = ff_triangle_or_park(p0, p1, p2, mask);
-					if (mask != 7u && mask != 0u) park_polygon(queue, counter, p0, p1, p2, mask, slot_d);
-					float3 q0 = mk3(fmaf(ltc.s00, p0.x, ltc.s02 * p0.z), ltc.s11 * p0.y, fmaf(ltc.s20, p0.x, ltc.s22 * p0.z));
-					float3 q1 = mk3(fmaf(ltc.s00, p1.x, ltc.s02 * p1.z), ltc.s11 * p1.y, fmaf(ltc.s20, p1.x, ltc.s22 * p1.z));
-					float3 q2 = mk3(fmaf(ltc.s00, p2.x, ltc.s02 * p2.z), ltc.s11 * p2.y, fmaf(ltc.s20, p2.x, ltc.s22 * p2.z));
-					sm_ff[slot_s] = ff_triangle_or_park(q0, q1, q2, mask);
-					if (mask != 7u && mask != 0u) park_polygon(queue, counter, q0, q1, q2, mask, slot_s);
-				}
-				// at most 64 items are parked per iteration: evaluate early when the queue could overflow
-				__syncwarp();
-				if (*(volatile int*) counter > RL_QUEUE - 64) drain_queue(queue, counter, sm_ff, lane);
+				// inactive lanes run the same arithmetic on a frame of zeros: their polygons have z = 0 and are never queued
+				seed = 1664525u * seed + 1013904223u;
+				int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
+				seed = 1664525u * seed + 1013904223u;   // the reservoir's draw, consumed in pass 2
+				const float4 A = table[3 * idx], B = table[3 * idx + 1], C = table[3 * idx + 2];
+				float3 p0, p1, p2;
+				p0.x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
+				p0.y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
+				p0.z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
+				p1.x = fmaf(ltc.rx.x, B.x, fmaf(ltc.rx.y, B.y, fmaf(ltc.rx.z, B.z, ltc.t.x)));
+				p1.y = fmaf(ltc.ry.x, B.x, fmaf(ltc.ry.y, B.y, fmaf(ltc.ry.z, B.z, ltc.t.y)));
+				p1.z = fmaf(ltc.rz.x, B.x, fmaf(ltc.rz.y, B.y, fmaf(ltc.rz.z, B.z, ltc.t.z)));
+				p2.x = fmaf(ltc.rx.x, C.x, fmaf(ltc.rx.y, C.y, fmaf(ltc.rx.z, C.z, ltc.t.x)));
+				p2.y = fmaf(ltc.ry.x, C.x, fmaf(ltc.ry.y, C.y, fmaf(ltc.ry.z, C.z, ltc.t.y)));
+				p2.z = fmaf(ltc.rz.x, C.x, fmaf(ltc.rz.y, C.y, fmaf(ltc.rz.z, C.z, ltc.t.z)));
+				const float3 q0 = mk3(fmaf(ltc.s00, p0.x, ltc.s02 * p0.z), ltc.s11 * p0.y, fmaf(ltc.s20, p0.x, ltc.s22 * p0.z));
+				const float3 q1 = mk3(fmaf(ltc.s00, p1.x, ltc.s02 * p1.z), ltc.s11 * p1.y, fmaf(ltc.s20, p1.x, ltc.s22 * p1.z));
+				const float3 q2 = mk3(fmaf(ltc.s00, p2.x, ltc.s02 * p2.z), ltc.s11 * p2.y, fmaf(ltc.s20, p2.x, ltc.s22 * p2.z));
+				push_polygon(queue, count_above, count_crossing, lt_mask, p0, p1, p2, dest);
+				push_polygon(queue, count_above, count_crossing, lt_mask, q0, q1, q2, dest + RL_CHUNK * 32u);
+				dest += 32u;
+				while (count_above >= 32u) { count_above -= 32u; drain<true>(queue, ff, count_above, 32u, lane); }
+				while (count_crossing >= 32u) { count_crossing -= 32u; drain<false>(queue, ff, RL_QUEUE - 32u - count_crossing, 32u, lane); }
 			}
-			drain_queue(queue, counter, sm_ff, lane);
-			// pass 3: the reservoir in the reference's order (reservoir.glsl:34-40), replaying the chunk's draws
+			if (count_above) drain<true>(queue, ff, 0u, count_above, lane);
+			if (count_crossing) drain<false>(queue, ff, RL_QUEUE - count_crossing, count_crossing, lane);
+			__syncwarp();
+			// pass 2: the reservoir in the reference's order (reservoir.glsl:34-40), replaying the chunk's draws
 			if (active) {
 				uint32_t replay = chunk_seed;
 				#pragma unroll 4
@@ -225,7 +240,7 @@ __global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(Scene
 					replay = 1664525u * replay + 1013904223u;
 					float r = __uint2float_rn(replay) * 2.3283064365386962890625e-10f;
 					const float* rec = (const float*) (table + 3 * idx);
-					float fd = sm_ff[j * 128 + tid], fs = sm_ff[(RL_CHUNK + j) * 128 + tid] * ltc.albedo;
+					float fd = ff[j * 32 + lane], fs = ff[(RL_CHUNK + j) * 32 + lane] * ltc.albedo;
 					float cr = fmaf(sp.diffuse_albedo.x, fd, fs) * rec[3], cg = fmaf(sp.diffuse_albedo.y, fd, fs) * rec[7], cb = fmaf(sp.diffuse_albedo.z, fd, fs) * rec[11];
 					float p_hat = approx_sqrt(fmaf(cr, cr, fmaf(cg, cg, cb * cb)));
 					float w = p_hat * Nf;
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(128, RL_FAST_MIN_BLOCKS) ris_ltc3_kernel(Scene
 					if (w > 0.0f && r * w_sum < w) { chosen = idx; chosen_p_hat = p_hat; }
 				}
 			}
-			__syncwarp();   // pass 1 of the next chunk overwrites sm_ff
+			__syncwarp();   // pass 1 of the next chunk overwrites the form factors
 		}
 		// ---- hand the winner to winner_kernel: light index, W = w_sum / (m p_hat) (shading_pass.frag.glsl:747-752), RNG state
 		if (active) {

@@ -8,5 +8,5 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:shade -s 2 -c 1 -f -o gpurun_out/prof_shade python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -5 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.err; cat gpurun_out/bench.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ris_ltc3 -s 2 -c 1 -f -o gpurun_out/prof_shade python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -n 5 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.err; cat gpurun_out/bench.json

@@ -131,6 +131,9 @@ int risltc_cuda_kat_noise(risltc_device_t* device, uint32_t width, uint32_t heig
 int risltc_cuda_kat_ltc_coefficients(risltc_device_t* device, const float* inputs /* count x 11: fresnel, roughness, pos, normal, outgoing */,
 	const float ltc_constants[6], float* out, uint32_t count);
 int risltc_cuda_kat_any_hit(risltc_device_t* device, const float* rays /* count x 8: o, tmin, d, tmax */, uint32_t* hits, uint32_t count);
+/* The shadow-ray kernels of the frame path on the same ray array (t_min is their fixed 1e-3): kind 4 = 4-wide quantised
+ * tree (default of render_frames), kind 2 = binary tree. */
+int risltc_cuda_kat_trace(risltc_device_t* device, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind);
 
 #ifdef __cplusplus
 }

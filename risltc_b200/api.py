@@ -188,3 +188,10 @@ class Device:
         hits = np.empty(r.shape[0], dtype=np.uint32)
         _check(lib().risltc_cuda_kat_any_hit(self.h, _p(r), _p(hits), C.c_uint32(r.shape[0])))
         return hits
+
+    def kat_trace(self, rays, kind=4):
+        """The frame path's shadow-ray kernel (4: 4-wide quantised tree, 2: binary tree) on an array of rays."""
+        r = np.ascontiguousarray(rays, dtype=np.float32)
+        hits = np.empty(r.shape[0], dtype=np.uint32)
+        _check(lib().risltc_cuda_kat_trace(self.h, _p(r), _p(hits), C.c_uint32(r.shape[0]), C.c_uint32(kind)))
+        return hits

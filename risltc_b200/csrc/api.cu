@@ -2,6 +2,7 @@
 #include "../../include/risltc_cuda.h"
 #include "kernels.cuh"
 #include "shade_fast.cuh"
+#include "trace4.cuh"
 #include "bvh_build.h"
 #include "clip_rotation_table.inc"
 #include <cstdio>
@@ -28,7 +29,7 @@ struct risltc_device_s {
 	// scene
 	uint2* positions = nullptr; ushort4* normals_uv = nullptr; uint8_t* material_indices = nullptr;
 	float4* materials = nullptr; float4* lights = nullptr; float4* lights_tri = nullptr; ushort4* ltc_rgba = nullptr; ushort2* ltc_rg = nullptr;
-	BvhNode* nodes = nullptr; BvhTri* tris = nullptr;
+	BvhNode* nodes = nullptr; BvhTri* tris = nullptr; Qbvh4Node* nodes4 = nullptr;
 	SceneView view = {};
 	float dequant_factor[3] = { 0, 0, 0 }, dequant_summand[3] = { 0, 0, 0 };
 	// variant + targets
@@ -39,7 +40,8 @@ struct risltc_device_s {
 	float4* own_accum = nullptr;
 	uint32_t ray_slots = 0, group_slots = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
-	int sm_count = 148, trace_resident = 1;
+	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
+	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
 	bool timed = false;
@@ -80,7 +82,9 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaMalloc(&d->px.ticket, sizeof(unsigned int)));
 	CU(cudaMemset(d->px.ticket, 0, sizeof(unsigned int)));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
-	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knob
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
+	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
+	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
 	return 0;
 }
@@ -95,8 +99,8 @@ static void free_targets(risltc_device_t* d) {
 }
 
 static void free_scene(risltc_device_t* d) {
-	cudaFree(d->positions); cudaFree(d->normals_uv); cudaFree(d->material_indices); cudaFree(d->nodes); cudaFree(d->tris);
-	d->positions = nullptr; d->normals_uv = nullptr; d->material_indices = nullptr; d->nodes = nullptr; d->tris = nullptr;
+	cudaFree(d->positions); cudaFree(d->normals_uv); cudaFree(d->material_indices); cudaFree(d->nodes); cudaFree(d->tris); cudaFree(d->nodes4);
+	d->positions = nullptr; d->normals_uv = nullptr; d->material_indices = nullptr; d->nodes = nullptr; d->tris = nullptr; d->nodes4 = nullptr;
 }
 
 extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
@@ -153,12 +157,18 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 		dt[slot].e1 = make_float4(e1x, e1y, e1z, 0.0f);
 		dt[slot].e2 = make_float4(e2x, e2y, e2z, 0.0f);
 	}
+	std::vector<Qbvh4NodeHost> dn4;
+	const uint32_t depth4 = build_qbvh4(nodes, dn4);
+	if (3u * depth4 + 1u > RL_T4_NSTACK + RL_T4_OVERFLOW) return fail("upload_scene: the acceleration structure is deeper than the traversal stack", nullptr);
+	static_assert(sizeof(Qbvh4NodeHost) == sizeof(Qbvh4Node), "node layouts");
+	CU(cudaMalloc(&d->nodes4, dn4.size() * sizeof(Qbvh4Node)));
+	CU(cudaMemcpy(d->nodes4, dn4.data(), dn4.size() * sizeof(Qbvh4Node), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&d->nodes, dn.size() * sizeof(BvhNode)));
 	CU(cudaMalloc(&d->tris, dt.size() * sizeof(BvhTri)));
 	CU(cudaMemcpy(d->nodes, dn.data(), dn.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d->tris, dt.data(), dt.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
 	d->view.positions = d->positions; d->view.normals_uv = d->normals_uv; d->view.material_indices = d->material_indices;
-	d->view.nodes = d->nodes; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
+	d->view.nodes = d->nodes; d->view.nodes4 = d->nodes4; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
 	return 0;
 }
 
@@ -380,7 +390,8 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant)) {
 			// (3) persistent any-hit traversal over all ray slots, (4) MIS sum + accumulation
 			const uint32_t ray_count = d->px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
+			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
+			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
 			resolve_kernel<true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
 			d->launches += 1;
 		}

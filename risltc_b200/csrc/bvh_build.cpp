@@ -146,3 +146,97 @@ void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeH
 	}
 	order.swap(b.order);
 }
+
+// ---- four children per node, 8-bit boxes
+namespace {
+struct Child4 { int ref; float lo[3], hi[3]; };
+
+float half_area(const Child4& c) {
+	float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+	return dx * dy + dy * dz + dz * dx;
+}
+void children_of(const BvhNodeHost& n, Child4& l, Child4& r) {
+	l.ref = n.left; r.ref = n.right;
+	for (int k = 0; k != 3; ++k) { l.lo[k] = n.left_lo[k]; l.hi[k] = n.left_hi[k]; r.lo[k] = n.right_lo[k]; r.hi[k] = n.right_hi[k]; }
+}
+}  // namespace
+
+uint32_t build_qbvh4(const std::vector<BvhNodeHost>& binary, std::vector<Qbvh4NodeHost>& nodes4) {
+	nodes4.clear();
+	nodes4.reserve(binary.size() / 2 + 1);
+	// work list of (binary node, slot of the 4-wide node that replaces it); children are emitted depth first so that a
+	// subtree stays close in memory
+	struct Item { int binary_node; uint32_t out, depth; };
+	uint32_t max_depth = 1;
+	std::vector<Item> todo;
+	nodes4.push_back(Qbvh4NodeHost());
+	todo.push_back({ 0, 0u, 1u });
+	while (!todo.empty()) {
+		Item it = todo.back(); todo.pop_back();
+		max_depth = std::max(max_depth, it.depth);
+		Child4 c[4]; int n = 2;
+		children_of(binary[it.binary_node], c[0], c[1]);
+		// the root of a one-leaf scene refers to the same leaf twice with an empty right box: keep only the left one
+		if (!(c[1].lo[0] <= c[1].hi[0])) n = 1;
+		while (n < 4) {
+			int pick = -1; float best = -1.0f;
+			for (int i = 0; i != n; ++i) if (c[i].ref >= 0 && half_area(c[i]) > best) { best = half_area(c[i]); pick = i; }
+			if (pick < 0) break;
+			Child4 l, r;
+			children_of(binary[c[pick].ref], l, r);
+			c[pick] = l; c[n++] = r;
+		}
+		double lo[3], hi[3];
+		for (int k = 0; k != 3; ++k) {
+			lo[k] = c[0].lo[k]; hi[k] = c[0].hi[k];
+			for (int i = 1; i != n; ++i) { lo[k] = std::min(lo[k], (double) c[i].lo[k]); hi[k] = std::max(hi[k], (double) c[i].hi[k]); }
+		}
+		Qbvh4NodeHost q;
+		memset(&q, 0, sizeof(q));
+		uint32_t exps = 0;
+		uint8_t qlo[3][4], qhi[3][4];
+		for (int k = 0; k != 3; ++k) {
+			double extent = std::max(hi[k] - lo[k], 1.0e-30);
+			int e = (int) std::ceil(std::log2(extent / 250.0));
+			for (;; ++e) {
+				if (e < -100) e = -100;
+				double s = std::ldexp(1.0, e);
+				float origin = (float) (lo[k] - 2.0 * s);
+				bool ok = true;
+				for (int i = 0; i != n && ok; ++i) {
+					// planes are evaluated on the device as origin + q * s with an error far below 0.05 steps
+					double a = std::floor(((double) c[i].lo[k] - (double) origin) / s - 0.05);
+					double b = std::ceil(((double) c[i].hi[k] - (double) origin) / s + 0.05);
+					if (a < 0.0 || b > 255.0 || !((double) origin + a * s <= (double) c[i].lo[k]) || !((double) origin + b * s >= (double) c[i].hi[k])) ok = false;
+					else { qlo[k][i] = (uint8_t) a; qhi[k][i] = (uint8_t) b; }
+				}
+				if (ok) {
+					memcpy(&q.w[k], &origin, 4);
+					exps |= (uint32_t) (e + 127) << (8 * k);
+					break;
+				}
+			}
+			for (int i = n; i != 4; ++i) { qlo[k][i] = 255; qhi[k][i] = 0; }   // inverted: never hit
+		}
+		q.w[3] = exps;
+		for (int k = 0; k != 3; ++k)
+			for (int i = 0; i != 4; ++i) {
+				q.w[4 + k] |= (uint32_t) qlo[k][i] << (8 * i);
+				q.w[7 + k] |= (uint32_t) qhi[k][i] << (8 * i);
+			}
+		for (int i = 0; i != 4; ++i) {
+			int ref = 0x7FFFFFFF;
+			if (i < n) {
+				if (c[i].ref < 0) ref = c[i].ref;
+				else {
+					ref = (int) nodes4.size();
+					nodes4.push_back(Qbvh4NodeHost());
+					todo.push_back({ c[i].ref, (uint32_t) ref, it.depth + 1u });
+				}
+			}
+			q.w[12 + i] = (uint32_t) ref;
+		}
+		nodes4[it.out] = q;
+	}
+	return max_depth;
+}

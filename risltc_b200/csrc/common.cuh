@@ -58,6 +58,17 @@ struct __align__(16) BvhNode {
 // .w of the first vector carries the primitive id (bit 31 = emitter flag).
 struct __align__(16) BvhTri { float4 v0, e1, e2; };
 
+// ---- 4-wide BVH for the any-hit kernel: 64 bytes hold FOUR children. Boxes are quantised to 8 bits per plane relative
+// to the node's own box (origin + q * 2^e per axis, rounded outwards at build time), which halves the bytes -- and the
+// L1 tag lookups, the measured limiter of the binary layout -- per child and halves the node visits per ray.
+struct __align__(16) Qbvh4Node {
+	uint4 a;    // origin x, y, z (float bits); w = biased exponents of the three step sizes, one per byte (x, y, z)
+	uint4 b;    // lo.x, lo.y, lo.z, hi.x: one byte per child each
+	uint4 c;    // hi.y, hi.z, unused x2
+	int4 refs;  // child references (>= 0 node, < 0 leaf as in BvhNode, RL_Q4_EMPTY = no child)
+};
+#define RL_Q4_EMPTY 0x7FFFFFFF
+
 struct SceneView {
 	const uint2* positions;          // T*3 quantised positions (mesh_t.positions)
 	const ushort4* normals_uv;       // T*3
@@ -68,6 +79,7 @@ struct SceneView {
 	uint32_t light_count, light_stride4;
 	const ushort4* ltc_rgba; const ushort2* ltc_rg; uint32_t ltc_res, ltc_layers;
 	const BvhNode* nodes; const BvhTri* tris; uint32_t triangle_count;
+	const Qbvh4Node* nodes4;         // the same tree collapsed to four children per node (shadow rays)
 };
 
 struct PixelBuffers {

@@ -172,3 +172,36 @@ extern "C" int risltc_cuda_kat_any_hit(risltc_device_t* d, const float* rays, ui
 	if (h.fetch(hits)) return fail("kat_any_hit: read-back failed", nullptr);
 	return 0;
 }
+
+// The production shadow-ray kernels (kind 4: trace4_kernel, 2: trace_kernel) on an array of rays with t_min = 1e-3:
+// the rays are laid out as one ray slot of `count` pixels, exactly what the shading kernels leave behind.
+__global__ void kat_trace_fill_kernel(const float* rays, float4* origin, float4* ray_a, float4* ray_b, uint32_t count) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float* r = rays + 8 * (size_t) i;
+	origin[i] = make_float4(r[0], r[1], r[2], 0.0f);
+	ray_a[i] = make_float4(r[4], r[5], r[6], r[7]);
+	ray_b[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+__global__ void kat_trace_read_kernel(const float4* ray_b, uint32_t* hits, uint32_t count) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) hits[i] = (ray_b[i].w == 2.0f) ? 1u : 0u;
+}
+extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind) {
+	if (use(d)) return 1;
+	if (!d->nodes || !d->nodes4) return fail("kat_trace: upload_scene first", nullptr);
+	if (kind != 2 && kind != 4) return fail("kat_trace: kind must be 2 or 4", nullptr);
+	DeviceArray<float> r; DeviceArray<uint32_t> h; DeviceArray<float4> og, ra, rb; DeviceArray<unsigned int> ticket;
+	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 1))
+		return fail("kat_trace: allocation failed", nullptr);
+	CU(cudaMemset(ticket.p, 0, sizeof(unsigned int)));
+	PixelBuffers px = {};
+	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
+	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
+	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote);
+	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
+	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
+	CU(cudaDeviceSynchronize());
+	if (h.fetch(hits)) return fail("kat_trace: read-back failed", nullptr);
+	return 0;
+}

@@ -1,0 +1,152 @@
+// trace4.cuh -- kernel (3), shadow rays (get_polygon_visibility, shading_pass.frag.glsl:112-129), second generation.
+//
+// Why it replaces trace_kernel (kernels.cuh) as the default: ncu showed the binary-tree kernel bound by the L1 data
+// pipe (l1tex__data_pipe_lsu_wavefronts 90 % of peak, profiles/r1_ncu_trace_kernel_l1.txt): every lane fetched 64 bytes
+// per TWO child boxes with four 16-byte loads, each of which costs a tag lookup per distinct node in the warp, and kept
+// its stacks in local memory, where lanes with different stack heights hit different lines. Here
+//   * a node holds FOUR children in the same 64 bytes (Qbvh4Node: boxes quantised to 8 bits relative to the node), so a
+//     ray needs half the node visits, half the dependent round trips and half the tag lookups;
+//   * a plane is decoded with one PRMT (the byte becomes the mantissa of a float in [1, 2)) and evaluated with one FFMA
+//     whose scale and offset are computed once per node; near / far planes are picked per axis by the sign of the ray
+//     direction, so a child costs 6 PRMT + 6 FFMA + 2 three-way min / max;
+//   * both stacks live in shared memory, one column per lane (bank = lane: one wavefront whatever the heights);
+//     a node stack deeper than RL_T4_NSTACK spills to local memory (never in the test scenes);
+//   * the triangle test and the decision rules are those of the oracle (tri_any_hit, bvh.cuh): hit / no-hit is
+//     independent of the shape of the tree, so the image is bit-identical to the binary-tree kernel's.
+#pragma once
+#include "kernels.cuh"
+
+namespace RL_NS {
+
+#define RL_T4_NSTACK 16     // node stack entries per lane in shared memory
+#define RL_T4_LSTACK 12     // leaf stack entries per lane in shared memory (the node track pauses when < 4 are free)
+#define RL_T4_OVERFLOW 80   // node stack entries per lane in local memory beyond RL_T4_NSTACK
+
+// plane byte k of `word` -> float 1 + q * 2^-15
+__device__ __forceinline__ float q4_plane(uint32_t word, uint32_t selector) { return __uint_as_float(__byte_perm(word, 0x3F800000u, selector)); }
+
+__global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote) {
+	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
+	__shared__ int sm_nstack[RL_T4_NSTACK][128];
+	__shared__ int sm_lstack[RL_T4_LSTACK][128];
+	int overflow[RL_T4_OVERFLOW];
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	float4 (*stage)[2] = sm_stage[warp];
+	uint32_t stage_next = 0, stage_count = 0;   // warp-uniform
+	bool exhausted = false, busy = false;
+	uint32_t ray = 0, tri_i = 0, tri_end = 0;
+	float3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), inv = mk3(0.0f, 0.0f, 0.0f), oi = mk3(0.0f, 0.0f, 0.0f);
+	float t_max = 0.0f;
+	int node = -1, nsp = 0, lsp = 0;
+	const float t_min = 1.0e-3f;
+	uint32_t ahead = 0;
+	if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
+	ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
+	while (true) {
+		const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
+		if (__popc(idle) >= RL_TRACE_REFILL || (idle && exhausted)) {
+			while (stage_next >= stage_count && !exhausted) {
+				const uint32_t base = ahead;
+				if (base >= ray_count) { exhausted = true; break; }
+				if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
+				ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
+				if (ahead + lane * 2u < ray_count) {
+					prefetch_l2(&px.ray_a[ahead + lane * 2u]); prefetch_l2(&px.ray_b[ahead + lane * 2u]);
+					prefetch_l2(&px.origin[(ahead + lane * 2u) % px.pixel_count]);
+				}
+				stage_next = stage_count = 0u;
+				#pragma unroll
+				for (uint32_t half = 0; half != 2u; ++half) {
+					const uint32_t r = base + half * 32u + lane;
+					bool valid = r < ray_count && __ldg(&((const float*) px.ray_b)[4 * (size_t) r + 3]) == 1.0f;
+					float4 ra = make_float4(0.0f, 0.0f, 1.0f, 0.0f), og = ra;
+					if (valid) { ra = px.ray_a[r]; og = px.origin[r % px.pixel_count]; valid = t_min < ra.w; }
+					const unsigned have = __ballot_sync(0xFFFFFFFFu, valid);
+					if (valid) {
+						const uint32_t slot = stage_count + __popc(have & ((1u << lane) - 1u));
+						stage[slot][0] = make_float4(og.x, og.y, og.z, ra.w);
+						stage[slot][1] = make_float4(ra.x, ra.y, ra.z, __uint_as_float(r));
+					}
+					stage_count += (uint32_t) __popc(have);
+				}
+				__syncwarp();
+			}
+			if (exhausted && stage_next >= stage_count && idle == 0xFFFFFFFFu) break;
+			if (!busy) {
+				const uint32_t mine = stage_next + __popc(idle & ((1u << lane) - 1u));
+				if (mine < stage_count) {
+					const float4 a0 = stage[mine][0], a1 = stage[mine][1];
+					ray = __float_as_uint(a1.w); busy = true;
+					o = mk3(a0.x, a0.y, a0.z); d = mk3(a1.x, a1.y, a1.z); t_max = a0.w;
+					// box tests only: the error of the approximate reciprocal is covered by the outward rounding of the boxes
+					inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
+					oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+					node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
+				}
+			}
+			stage_next = min(stage_next + (uint32_t) __popc(idle), stage_count);
+			__syncwarp();
+		}
+		const bool node_ready = busy && node >= 0 && lsp <= RL_T4_LSTACK - 4;
+		const bool tri_pending = busy && (tri_i != tri_end || lsp != 0);
+		const unsigned node_votes = __ballot_sync(0xFFFFFFFFu, node_ready), tri_votes = __ballot_sync(0xFFFFFFFFu, tri_pending);
+		const bool run_tri = (uint32_t) __popc(tri_votes) >= tri_vote || node_votes == 0u;
+		// ---- track A: one node = four child boxes
+		if (node_ready) {
+			const Qbvh4Node* np = s.nodes4 + node;
+			const uint4 na = __ldg(&np->a), nb = __ldg(&np->b);
+			const uint2 nc = __ldg((const uint2*) &np->c);
+			const int4 refs = __ldg(&np->refs);
+			// plane = origin + q * 2^e; with v = 1 + q * 2^-15 (see q4_plane): t = v * S + B, S = 2^(e + 15) / d, B = (origin - o) / d - S
+			const float sx = __uint_as_float(((na.w & 0xFFu) + 15u) << 23) * inv.x;
+			const float sy = __uint_as_float((((na.w >> 8) & 0xFFu) + 15u) << 23) * inv.y;
+			const float sz = __uint_as_float((((na.w >> 16) & 0xFFu) + 15u) << 23) * inv.z;
+			const float bx = fmaf(__uint_as_float(na.x), inv.x, -oi.x) - sx;
+			const float by = fmaf(__uint_as_float(na.y), inv.y, -oi.y) - sy;
+			const float bz = fmaf(__uint_as_float(na.z), inv.z, -oi.z) - sz;
+			// the plane the ray enters through is the low one where the direction is positive
+			const bool neg_x = inv.x < 0.0f, neg_y = inv.y < 0.0f, neg_z = inv.z < 0.0f;
+			const uint32_t near_x = neg_x ? nb.w : nb.x, far_x = neg_x ? nb.x : nb.w;
+			const uint32_t near_y = neg_y ? nc.x : nb.y, far_y = neg_y ? nb.y : nc.x;
+			const uint32_t near_z = neg_z ? nc.y : nb.z, far_z = neg_z ? nb.z : nc.y;
+			int next = -1;
+			#pragma unroll
+			for (int c = 0; c != 4; ++c) {
+				const uint32_t sel = 0x7604u | ((uint32_t) c << 4);
+				const float t0 = fmaxf(fmaxf(fmaf(q4_plane(near_x, sel), sx, bx), fmaf(q4_plane(near_y, sel), sy, by)), fmaxf(fmaf(q4_plane(near_z, sel), sz, bz), t_min));
+				const float t1 = fminf(fminf(fmaf(q4_plane(far_x, sel), sx, bx), fmaf(q4_plane(far_y, sel), sy, by)), fminf(fmaf(q4_plane(far_z, sel), sz, bz), t_max));
+				const int ref = (c == 0) ? refs.x : (c == 1) ? refs.y : (c == 2) ? refs.z : refs.w;
+				if (t0 <= t1 && ref != RL_Q4_EMPTY) {
+					if (ref < 0) sm_lstack[lsp++][tid] = ref;
+					else {
+						if (next >= 0) {
+							if (nsp < RL_T4_NSTACK) sm_nstack[nsp][tid] = next; else overflow[nsp - RL_T4_NSTACK] = next;
+							++nsp;
+						}
+						next = ref;
+					}
+				}
+			}
+			if (next < 0 && nsp) {
+				--nsp;
+				next = (nsp < RL_T4_NSTACK) ? sm_nstack[nsp][tid] : overflow[nsp - RL_T4_NSTACK];
+			}
+			node = next;
+		}
+		// ---- track B: one triangle
+		if (run_tri && tri_pending) {
+			if (tri_i == tri_end) {
+				const uint32_t ref = ~(uint32_t) sm_lstack[--lsp][tid];
+				tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
+			}
+			if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
+				((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
+				busy = false;
+			}
+			++tri_i;
+		}
+		if (busy && node < 0 && tri_i == tri_end && lsp == 0) busy = false;   // nothing left on either track: the ray reaches the light
+	}
+}
+
+}  // namespace RL_NS

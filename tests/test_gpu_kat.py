@@ -98,4 +98,8 @@ def test_any_hit_matches_oracle_bit_for_bit(device, ltc_tables):
     got = device.kat_any_hit(rays)
     want = np.array([osc.any_hit(r[0:3], r[4:7], float(r[3]), float(r[7])) for r in rays], dtype=np.uint32)
     assert np.array_equal(got, want), f"{np.count_nonzero(got != want)} of {n} any-hit decisions differ"
+    # the shadow-ray kernels of the frame path: the 4-wide quantised tree (default) and the binary tree
+    for kind in (4, 2):
+        got = device.kat_trace(rays, kind)
+        assert np.array_equal(got, want), f"trace kernel {kind}: {np.count_nonzero(got != want)} of {n} any-hit decisions differ"
     assert 0.05 < want.mean() < 0.98

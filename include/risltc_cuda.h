@@ -134,6 +134,10 @@ int risltc_cuda_kat_any_hit(risltc_device_t* device, const float* rays /* count 
 /* The shadow-ray kernels of the frame path on the same ray array (t_min is their fixed 1e-3): kind 4 = 4-wide quantised
  * tree (default of render_frames), kind 2 = binary tree. */
 int risltc_cuda_kat_trace(risltc_device_t* device, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind);
+/* Exhaustive device-side check of the kernels' hand-written exactly rounded sequences against the IEEE operations they
+ * stand for: [0] inversesqrt vs 1 / sqrt over every float of its fast range, [1] unorm16 vs x / 65535 for 0..65535,
+ * [2] inversesqrt over every other bit pattern. All three must be 0. */
+int risltc_cuda_kat_exact_math(risltc_device_t* device, uint64_t mismatches[3]);
 
 #ifdef __cplusplus
 }

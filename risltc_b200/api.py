@@ -189,6 +189,11 @@ class Device:
         _check(lib().risltc_cuda_kat_any_hit(self.h, _p(r), _p(hits), C.c_uint32(r.shape[0])))
         return hits
 
+    def kat_exact_math(self):
+        out = (C.c_uint64 * 3)()
+        _check(lib().risltc_cuda_kat_exact_math(self.h, out))
+        return [int(v) for v in out]
+
     def kat_trace(self, rays, kind=4):
         """The frame path's shadow-ray kernel (4: 4-wide quantised tree, 2: binary tree) on an array of rays."""
         r = np.ascontiguousarray(rays, dtype=np.float32)

@@ -41,6 +41,7 @@ struct risltc_device_s {
 	uint32_t ray_slots = 0, group_slots = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
+	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
@@ -84,6 +85,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
+	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
 	return 0;
@@ -134,7 +136,7 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	std::vector<float> verts;
 	dequantize_mesh_for_bvh(quantized_positions, T, factor, summand, verts);
 	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
-	uint32_t max_leaf = 4;
+	uint32_t max_leaf = 2;   // measured best for the 4-wide any-hit kernel (a triangle test costs about as much as three box tests)
 	if (const char* e = getenv("RISLTC_BVH_LEAF")) max_leaf = (uint32_t) atoi(e);
 	build_bvh(verts.data(), T, nodes, order, max_leaf);
 	std::vector<BvhNode> dn(nodes.size());
@@ -159,7 +161,7 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	}
 	std::vector<Qbvh4NodeHost> dn4;
 	const uint32_t depth4 = build_qbvh4(nodes, dn4);
-	if (3u * depth4 + 1u > RL_T4_NSTACK + RL_T4_OVERFLOW) return fail("upload_scene: the acceleration structure is deeper than the traversal stack", nullptr);
+	if (3u * depth4 + 1u > RL_T4_OVERFLOW) return fail("upload_scene: the acceleration structure is deeper than the traversal stack", nullptr);
 	static_assert(sizeof(Qbvh4NodeHost) == sizeof(Qbvh4Node), "node layouts");
 	CU(cudaMalloc(&d->nodes4, dn4.size() * sizeof(Qbvh4Node)));
 	CU(cudaMemcpy(d->nodes4, dn4.data(), dn4.size() * sizeof(Qbvh4Node), cudaMemcpyHostToDevice));
@@ -390,7 +392,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant)) {
 			// (3) persistent any-hit traversal over all ray slots, (4) MIS sum + accumulation
 			const uint32_t ray_count = d->px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
+			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote, d->refill);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
 			resolve_kernel<true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
 			d->launches += 1;

@@ -193,7 +193,7 @@ uint32_t build_qbvh4(const std::vector<BvhNodeHost>& binary, std::vector<Qbvh4No
 		}
 		Qbvh4NodeHost q;
 		memset(&q, 0, sizeof(q));
-		uint32_t exps = 0;
+		const int scale_word[3] = { 3, 10, 11 };
 		uint8_t qlo[3][4], qhi[3][4];
 		for (int k = 0; k != 3; ++k) {
 			double extent = std::max(hi[k] - lo[k], 1.0e-30);
@@ -212,13 +212,13 @@ uint32_t build_qbvh4(const std::vector<BvhNodeHost>& binary, std::vector<Qbvh4No
 				}
 				if (ok) {
 					memcpy(&q.w[k], &origin, 4);
-					exps |= (uint32_t) (e + 127) << (8 * k);
+					float scale = (float) std::ldexp(1.0, e + 15);
+					memcpy(&q.w[scale_word[k]], &scale, 4);
 					break;
 				}
 			}
 			for (int i = n; i != 4; ++i) { qlo[k][i] = 255; qhi[k][i] = 0; }   // inverted: never hit
 		}
-		q.w[3] = exps;
 		for (int k = 0; k != 3; ++k)
 			for (int i = 0; i != 4; ++i) {
 				q.w[4 + k] |= (uint32_t) qlo[k][i] << (8 * i);

@@ -62,9 +62,9 @@ struct __align__(16) BvhTri { float4 v0, e1, e2; };
 // to the node's own box (origin + q * 2^e per axis, rounded outwards at build time), which halves the bytes -- and the
 // L1 tag lookups, the measured limiter of the binary layout -- per child and halves the node visits per ray.
 struct __align__(16) Qbvh4Node {
-	uint4 a;    // origin x, y, z (float bits); w = biased exponents of the three step sizes, one per byte (x, y, z)
+	uint4 a;    // origin x, y, z; w = 2^15 * step of the x planes (all float bits; steps are powers of two)
 	uint4 b;    // lo.x, lo.y, lo.z, hi.x: one byte per child each
-	uint4 c;    // hi.y, hi.z, unused x2
+	uint4 c;    // hi.y, hi.z; 2^15 * step of the y planes, of the z planes (float bits)
 	int4 refs;  // child references (>= 0 node, < 0 leaf as in BvhNode, RL_Q4_EMPTY = no child)
 };
 #define RL_Q4_EMPTY 0x7FFFFFFF
@@ -111,7 +111,34 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return mk2(a.x - b.
 __device__ __forceinline__ float2 scale2(float2 a, float s) { return mk2(a.x * s, a.y * s); }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 // GLSL inversesqrt / normalize as the oracle defines them: 1/sqrt (both correctly rounded), then multiply
-__device__ __forceinline__ float inversesqrt(float x) { return 1.0f / sqrtf(x); }
+__device__ __noinline__ float inversesqrt_ieee(float x) { return 1.0f / sqrtf(x); }
+// The same value, RN(1 / RN(sqrt(x))), without the two IEEE sequences and their slow-path branches: one MUFU.RSQ seeds
+// both the square root (two residual corrections) and its reciprocal (two Newton steps), all in FMAs. Bit-identical to
+// inversesqrt_ieee for EVERY float in [2^-64, 2^64) -- verified exhaustively on the device (risltc_cuda_kat_exact_math,
+// tests/test_gpu_kat.py) -- and handed to it outside that range.
+__device__ __forceinline__ float inversesqrt(float x) {
+	if ((__float_as_uint(x) - 0x1F800000u) >= 0x40000000u) return inversesqrt_ieee(x);
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	const float h = __fmul_rn(0.5f, y);
+	float s = __fmul_rn(x, y);
+	s = __fmaf_rn(__fmaf_rn(-s, s, x), h, s);
+	s = __fmaf_rn(__fmaf_rn(-s, s, x), h, s);
+	float r = __fmaf_rn(__fmaf_rn(-s, y, 1.0f), y, y);
+	r = __fmaf_rn(__fmaf_rn(-s, r, 1.0f), r, r);
+	// the one mantissa where Newton's last sum is an exact tie and rounds to even, wrongly: s = 2^k (2 - 2^-23), whose
+	// reciprocal 2^-(k+1) (1 + 2^-24 + ...) rounds UP to 2^-(k+1) (1 + 2^-23)
+	const uint32_t sb = __float_as_uint(s);
+	if ((sb & 0x7FFFFFu) == 0x7FFFFFu) r = __uint_as_float(0x7E800001u - (sb & 0x7F800000u));
+	return r;
+}
+// x / 65535 for an integer 0 <= x <= 65535, correctly rounded (checked for all 65536 values by the same device test):
+// product with the rounded reciprocal plus one residual correction instead of an IEEE division
+__device__ __forceinline__ float unorm16(uint32_t q) {
+	const float x = (float) q, c = 1.0f / 65535.0f;
+	const float q0 = __fmul_rn(x, c);
+	return __fmaf_rn(__fmaf_rn(-q0, 65535.0f, x), c, q0);
+}
 // single MUFU instructions (about 1 ulp, denormals flushed) for the paths where the rounding is free
 __device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -198,10 +198,42 @@ extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint
 	PixelBuffers px = {};
 	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
 	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
-	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote);
+	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
 	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
 	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
 	CU(cudaDeviceSynchronize());
 	if (h.fetch(hits)) return fail("kat_trace: read-back failed", nullptr);
+	return 0;
+}
+
+// Exhaustive checks of the hand-written exactly rounded sequences of common.cuh against the IEEE operations they replace:
+// out[0] = floats in [2^-64, 2^64) whose inversesqrt differs from 1 / sqrt, out[1] = values of 0..65535 whose unorm16
+// differs from x / 65535, out[2] = floats outside the fast range (or special) whose inversesqrt differs bitwise.
+__global__ void kat_exact_math_kernel(unsigned long long* out) {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	uint32_t bad_fast = 0, bad_unorm = 0, bad_other = 0;
+	for (uint64_t b = blockIdx.x * blockDim.x + threadIdx.x; b < 0x100000000ull; b += stride) {
+		const float x = __uint_as_float((uint32_t) b);
+		const uint32_t got = __float_as_uint(inversesqrt(x)), want = __float_as_uint(__frcp_rn(__fsqrt_rn(x)));
+		const bool fast = ((uint32_t) b - 0x1F800000u) < 0x40000000u;
+		const bool same = got == want || (isnan(__uint_as_float(got)) && isnan(__uint_as_float(want)));
+		if (!same) { if (fast) ++bad_fast; else ++bad_other; unsigned long long k = atomicAdd(&out[3], 1ull); if (k < 12) out[4 + k] = ((unsigned long long) got << 32) | (uint32_t) b; }
+		if (b < 65536u && __float_as_uint(unorm16((uint32_t) b)) != __float_as_uint(__fdiv_rn((float) (uint32_t) b, 65535.0f))) ++bad_unorm;
+	}
+	if (bad_fast) atomicAdd(&out[0], (unsigned long long) bad_fast);
+	if (bad_unorm) atomicAdd(&out[1], (unsigned long long) bad_unorm);
+	if (bad_other) atomicAdd(&out[2], (unsigned long long) bad_other);
+}
+extern "C" int risltc_cuda_kat_exact_math(risltc_device_t* d, uint64_t mismatches[3]) {
+	if (use(d)) return 1;
+	DeviceArray<unsigned long long> o;
+	if (o.init(nullptr, 16)) return fail("kat_exact_math: allocation failed", nullptr);
+	CU(cudaMemset(o.p, 0, 16 * sizeof(unsigned long long)));
+	kat_exact_math_kernel<<<d->sm_count * 8, 256>>>(o.p);
+	CU(cudaDeviceSynchronize());
+	unsigned long long h[16];
+	if (o.fetch(h)) return fail("kat_exact_math: read-back failed", nullptr);
+	for (int i = 0; i != 3; ++i) mismatches[i] = h[i];
+	for (int i = 4; i != 16; ++i) if (h[i]) printf("kat_exact_math: x = 0x%08x, inversesqrt gives 0x%08x\n", (unsigned) h[i], (unsigned) (h[i] >> 32));
 	return 0;
 }

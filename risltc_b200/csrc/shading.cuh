@@ -73,8 +73,8 @@ __device__ ShadingPoint reconstruct_shading_point(const SceneView& s, const Fram
 	for (int i = 0; i != 3; ++i) {
 		p[i] = decode_position(__ldg(&s.positions[prim * 3u + i]), f.dequant_factor, f.dequant_summand);
 		ushort4 a = __ldg(&s.normals_uv[prim * 3u + i]);
-		n[i] = decode_normal((float) a.x / 65535.0f, (float) a.y / 65535.0f);
-		uv[i] = mk2(fmaf((float) a.z / 65535.0f, 8.0f, 0.0f), fmaf((float) a.w / 65535.0f, -8.0f, 1.0f));
+		n[i] = decode_normal(unorm16(a.x), unorm16(a.y));
+		uv[i] = mk2(fmaf(unorm16(a.z), 8.0f, 0.0f), fmaf(unorm16(a.w), -8.0f, 1.0f));
 	}
 	float3 origin = mk3(f.camera[0], f.camera[1], f.camera[2]);
 	float3 e0 = sub3(p[1], p[0]), e1 = sub3(p[2], p[0]);
@@ -142,7 +142,7 @@ __device__ void ltc_fetch(const SceneView& s, float u, float v, float layer_coor
 	uint32_t i00 = base + y0 * res + x0, i10 = base + y0 * res + x1, i01 = base + y1 * res + x0, i11 = base + y1 * res + x1;
 	ushort4 a00 = __ldg(&s.ltc_rgba[i00]), a10 = __ldg(&s.ltc_rgba[i10]), a01 = __ldg(&s.ltc_rgba[i01]), a11 = __ldg(&s.ltc_rgba[i11]);
 	ushort2 b00 = __ldg(&s.ltc_rg[i00]), b10 = __ldg(&s.ltc_rg[i10]), b01 = __ldg(&s.ltc_rg[i01]), b11 = __ldg(&s.ltc_rg[i11]);
-	#define RL_BILERP(c00_, c10_, c01_, c11_) (w00 * ((float) (c00_) / 65535.0f) + w10 * ((float) (c10_) / 65535.0f) + w01 * ((float) (c01_) / 65535.0f) + w11 * ((float) (c11_) / 65535.0f))
+	#define RL_BILERP(c00_, c10_, c01_, c11_) (w00 * unorm16(c00_) + w10 * unorm16(c10_) + w01 * unorm16(c01_) + w11 * unorm16(c11_))
 	out[0] = RL_BILERP(a00.x, a10.x, a01.x, a11.x);
 	out[1] = RL_BILERP(a00.y, a10.y, a01.y, a11.y);
 	out[2] = RL_BILERP(a00.z, a10.z, a01.z, a11.z);

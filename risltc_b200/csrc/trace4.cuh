@@ -8,7 +8,7 @@
 //     ray needs half the node visits, half the dependent round trips and half the tag lookups;
 //   * a plane is decoded with one PRMT (the byte becomes the mantissa of a float in [1, 2)) and evaluated with one FFMA
 //     whose scale and offset are computed once per node; near / far planes are picked per axis by the sign of the ray
-//     direction, so a child costs 6 PRMT + 6 FFMA + 2 three-way min / max;
+//     direction, so a child costs 6 PRMT + 6 FFMA + 2 FMNMX3 + 2 FMNMX, and its hit is dispatched without a branch;
 //   * both stacks live in shared memory, one column per lane (bank = lane: one wavefront whatever the heights);
 //     a node stack deeper than RL_T4_NSTACK spills to local memory (never in the test scenes);
 //   * the triangle test and the decision rules are those of the oracle (tri_any_hit, bvh.cuh): hit / no-hit is
@@ -20,12 +20,14 @@ namespace RL_NS {
 
 #define RL_T4_NSTACK 16     // node stack entries per lane in shared memory
 #define RL_T4_LSTACK 12     // leaf stack entries per lane in shared memory (the node track pauses when < 4 are free)
-#define RL_T4_OVERFLOW 80   // node stack entries per lane in local memory beyond RL_T4_NSTACK
+#define RL_T4_OVERFLOW 88   // node stack entries per lane in local memory (spilled from / refilled into the shared part 8 at a time)
 
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 // plane byte k of `word` -> float 1 + q * 2^-15
 __device__ __forceinline__ float q4_plane(uint32_t word, uint32_t selector) { return __uint_as_float(__byte_perm(word, 0x3F800000u, selector)); }
 
-__global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote) {
+__global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote, uint32_t refill) {
 	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
 	__shared__ int sm_nstack[RL_T4_NSTACK][128];
 	__shared__ int sm_lstack[RL_T4_LSTACK][128];
@@ -37,14 +39,14 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 	uint32_t ray = 0, tri_i = 0, tri_end = 0;
 	float3 o = mk3(0.0f, 0.0f, 0.0f), d = mk3(0.0f, 0.0f, 1.0f), inv = mk3(0.0f, 0.0f, 0.0f), oi = mk3(0.0f, 0.0f, 0.0f);
 	float t_max = 0.0f;
-	int node = -1, nsp = 0, lsp = 0;
+	int node = -1, nsp = 0, lsp = 0, spilled = 0;
 	const float t_min = 1.0e-3f;
 	uint32_t ahead = 0;
 	if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
 	ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
 	while (true) {
 		const unsigned idle = __ballot_sync(0xFFFFFFFFu, !busy);
-		if (__popc(idle) >= RL_TRACE_REFILL || (idle && exhausted)) {
+		if ((uint32_t) __popc(idle) >= refill || (idle && exhausted)) {
 			while (stage_next >= stage_count && !exhausted) {
 				const uint32_t base = ahead;
 				if (base >= ray_count) { exhausted = true; break; }
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 					// box tests only: the error of the approximate reciprocal is covered by the outward rounding of the boxes
 					inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
 					oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-					node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
+					node = 0; nsp = 0; lsp = 0; spilled = 0; tri_i = tri_end = 0u;
 				}
 			}
 			stage_next = min(stage_next + (uint32_t) __popc(idle), stage_count);
@@ -91,16 +93,14 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 		const bool tri_pending = busy && (tri_i != tri_end || lsp != 0);
 		const unsigned node_votes = __ballot_sync(0xFFFFFFFFu, node_ready), tri_votes = __ballot_sync(0xFFFFFFFFu, tri_pending);
 		const bool run_tri = (uint32_t) __popc(tri_votes) >= tri_vote || node_votes == 0u;
-		// ---- track A: one node = four child boxes
+		// ---- track A: one node = four child boxes. No divergent branches: every child stores its reference to the top of
+		// both stacks and CLAIMS the slot only if it belongs there; the last inner hit stays in a register as the next node.
 		if (node_ready) {
 			const Qbvh4Node* np = s.nodes4 + node;
-			const uint4 na = __ldg(&np->a), nb = __ldg(&np->b);
-			const uint2 nc = __ldg((const uint2*) &np->c);
+			const uint4 na = __ldg(&np->a), nb = __ldg(&np->b), nc = __ldg(&np->c);
 			const int4 refs = __ldg(&np->refs);
-			// plane = origin + q * 2^e; with v = 1 + q * 2^-15 (see q4_plane): t = v * S + B, S = 2^(e + 15) / d, B = (origin - o) / d - S
-			const float sx = __uint_as_float(((na.w & 0xFFu) + 15u) << 23) * inv.x;
-			const float sy = __uint_as_float((((na.w >> 8) & 0xFFu) + 15u) << 23) * inv.y;
-			const float sz = __uint_as_float((((na.w >> 16) & 0xFFu) + 15u) << 23) * inv.z;
+			// plane = origin + q * step; with v = 1 + q * 2^-15 (q4_plane): t = v * S + B, S = (2^15 step) / d, B = (origin - o) / d - S
+			const float sx = __uint_as_float(na.w) * inv.x, sy = __uint_as_float(nc.z) * inv.y, sz = __uint_as_float(nc.w) * inv.z;
 			const float bx = fmaf(__uint_as_float(na.x), inv.x, -oi.x) - sx;
 			const float by = fmaf(__uint_as_float(na.y), inv.y, -oi.y) - sy;
 			const float bz = fmaf(__uint_as_float(na.z), inv.z, -oi.z) - sz;
@@ -109,29 +109,39 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 			const uint32_t near_x = neg_x ? nb.w : nb.x, far_x = neg_x ? nb.x : nb.w;
 			const uint32_t near_y = neg_y ? nc.x : nb.y, far_y = neg_y ? nb.y : nc.x;
 			const uint32_t near_z = neg_z ? nc.y : nb.z, far_z = neg_z ? nb.z : nc.y;
+			if (nsp > RL_T4_NSTACK - 4) {
+				// (almost) never: the shared part of the node stack could overflow -> move its 8 oldest entries to local memory
+				#pragma unroll 1
+				for (int i = 0; i != 8; ++i) overflow[spilled + i] = sm_nstack[i][tid];
+				#pragma unroll 1
+				for (int i = 8; i < nsp; ++i) sm_nstack[i - 8][tid] = sm_nstack[i][tid];
+				spilled += 8; nsp -= 8;
+			}
 			int next = -1;
 			#pragma unroll
 			for (int c = 0; c != 4; ++c) {
 				const uint32_t sel = 0x7604u | ((uint32_t) c << 4);
-				const float t0 = fmaxf(fmaxf(fmaf(q4_plane(near_x, sel), sx, bx), fmaf(q4_plane(near_y, sel), sy, by)), fmaxf(fmaf(q4_plane(near_z, sel), sz, bz), t_min));
-				const float t1 = fminf(fminf(fmaf(q4_plane(far_x, sel), sx, bx), fmaf(q4_plane(far_y, sel), sy, by)), fminf(fmaf(q4_plane(far_z, sel), sz, bz), t_max));
+				const float t0 = fmaxf(max3(fmaf(q4_plane(near_x, sel), sx, bx), fmaf(q4_plane(near_y, sel), sy, by), fmaf(q4_plane(near_z, sel), sz, bz)), t_min);
+				const float t1 = fminf(min3(fmaf(q4_plane(far_x, sel), sx, bx), fmaf(q4_plane(far_y, sel), sy, by), fmaf(q4_plane(far_z, sel), sz, bz)), t_max);
 				const int ref = (c == 0) ? refs.x : (c == 1) ? refs.y : (c == 2) ? refs.z : refs.w;
-				if (t0 <= t1 && ref != RL_Q4_EMPTY) {
-					if (ref < 0) sm_lstack[lsp++][tid] = ref;
-					else {
-						if (next >= 0) {
-							if (nsp < RL_T4_NSTACK) sm_nstack[nsp][tid] = next; else overflow[nsp - RL_T4_NSTACK] = next;
-							++nsp;
-						}
-						next = ref;
-					}
-				}
+				const bool hit = t0 <= t1 && ref != RL_Q4_EMPTY;
+				const bool leaf = hit && ref < 0, inner = hit && ref >= 0;
+				sm_lstack[lsp][tid] = ref;
+				lsp += leaf ? 1 : 0;
+				const bool push = inner && next >= 0;
+				sm_nstack[nsp][tid] = next;
+				nsp += push ? 1 : 0;
+				next = inner ? ref : next;
 			}
-			if (next < 0 && nsp) {
-				--nsp;
-				next = (nsp < RL_T4_NSTACK) ? sm_nstack[nsp][tid] : overflow[nsp - RL_T4_NSTACK];
+			if (next < 0 && nsp == 0 && spilled != 0) {
+				spilled -= 8; nsp = 8;
+				#pragma unroll 1
+				for (int i = 0; i != 8; ++i) sm_nstack[i][tid] = overflow[spilled + i];
 			}
-			node = next;
+			const bool pop = next < 0 && nsp > 0;
+			nsp -= pop ? 1 : 0;
+			const int top = sm_nstack[nsp][tid];
+			node = pop ? top : next;
 		}
 		// ---- track B: one triangle
 		if (run_tri && tri_pending) {

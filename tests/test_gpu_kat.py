@@ -103,3 +103,8 @@ def test_any_hit_matches_oracle_bit_for_bit(device, ltc_tables):
         got = device.kat_trace(rays, kind)
         assert np.array_equal(got, want), f"trace kernel {kind}: {np.count_nonzero(got != want)} of {n} any-hit decisions differ"
     assert 0.05 < want.mean() < 0.98
+
+
+def test_exactly_rounded_sequences_exhaustively(device):
+    """inversesqrt (RSQ seed + FMA corrections) == 1 / sqrt for every float, unorm16 == x / 65535 for every 16-bit value."""
+    assert device.kat_exact_math() == [0, 0, 0]

@@ -42,6 +42,7 @@ struct risltc_device_s {
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
 	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
+	uint32_t winner_threads = 256;   // CTA size of the phase-synchronous winner kernel (128, 256 or 512; 512 threads resident per SM)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
@@ -85,6 +86,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
+	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128) ? (uint32_t) t : 256u; }
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
@@ -354,7 +356,15 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f) {
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
 		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
 		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
-		winner_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
+		{
+			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles
+			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
+			uint32_t wctas = (512u / threads) * (uint32_t) d->sm_count;
+			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
+			if (threads == 512) winner_kernel<512><<<wctas, 512, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256><<<wctas, 256, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+			else winner_kernel<128><<<wctas, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		}
 		d->launches += 1;
 	}
 	else if (v.max_light_vertices == 3) {

@@ -265,27 +265,106 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 }
 
 // The winner's estimator (evaluate_polygonal_light_shading_peters, shading_pass.frag.glsl:292-397) for the light that
-// ris_ltc3_kernel chose; shadow rays are deferred to the resolve kernel. Every operation here is rounded as in the oracle.
-__global__ void __launch_bounds__(128) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out) {
-	uint32_t x, row, y;
-	if (!tile_pixel(f, st, x, row, y)) return;
-	const uint32_t pixel = row * f.width + x;
-	const uint32_t prim = out.visibility[pixel];
-	if (prim == 0xFFFFFFFFu || (prim >> 31) != 0u) return;   // base / origin were written by ris_ltc3_kernel
-	const uint4 pick = out.pick[pixel];
+// ris_ltc3_kernel chose; shadow rays are deferred to the trace kernel. Every operation here is rounded as in the oracle.
+//
+// Organisation: the estimator is ~80 KB of straight-line SASS, far beyond the 32 KB instruction cache of an SM, and ncu
+// showed the first version (one pixel per thread, 128-thread CTAs running through it at their own pace) stalled on
+// instruction fetch (no_instruction 3.8 warps per issue, issue-active 47 %). Here a CTA of RL_WIN_THREADS walks through
+// the estimator in PHASES separated by __syncthreads(), so that all its warps execute the same < 32 KB of code at the same
+// time and every instruction line is fetched once per CTA and phase instead of once per warp: (A) shading point, LTC frame,
+// light, both clipped polygons; (B) PSA preparation of the diffuse polygon; (C) of the specular polygon (the same code,
+// still cached); (D) diffuse sample; (E) specular sample (same code); (F) densities, BRDF, MIS weights, ray records.
+// The draws keep the reference's order (diffuse pair, then specular pair only if its solid angle is positive).
+template <int RL_WIN_THREADS>
+__global__ void __launch_bounds__(RL_WIN_THREADS, 512 / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
 	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
-	ShadingPoint sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
-	float3 carry = mk3(0.0f, 0.0f, 0.0f);
-	if ((int) pick.x >= 0) {
-		float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
-		LtcFrame ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
-		Light<3> light = load_light<3>(s, pick.x);
-		ShadeContext<3, true> c = { s, f, var, out, pixel, pick.z, 0u };
-		carry = sample_light<3, true>(c, sp, ltc, light, true, false, 0u);
+	// a warp owns 8x4 pixel tiles; all warps of the CTA run the same number of rounds (barriers inside)
+	for (uint32_t base = blockIdx.x * warps; base < tile_count; base += gridDim.x * warps) {
+		const uint32_t tile = base + warp;
+		const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u);
+		const uint32_t row = (tile / tiles_x) * 4u + (lane >> 3);
+		const bool inside = tile < tile_count && x < f.width && row < st.owned_rows;
+		const uint32_t y = st.global_row(inside ? row : 0u);
+		const uint32_t pixel = row * f.width + x;
+		const uint32_t prim = (inside && y < f.height) ? out.visibility[pixel] : 0xFFFFFFFFu;
+		const bool shaded = prim != 0xFFFFFFFFu && (prim >> 31) == 0u;   // base / origin of the other pixels were written by ris_ltc3_kernel
+		uint4 pick = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+		if (shaded) pick = out.pick[pixel];
+		bool live = shaded && (int) pick.x >= 0;
+		// ---- (A)
+		ShadingPoint sp;
+		LtcFrame ltc;
+		Light<3> light;
+		Techniques<3> t;
+		float3 pv[4], pq[4];
+		uint32_t vc_d = 0, vc_s = 0;
+		if (shaded) sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
+		if (live) {
+			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+			light = load_light<3>(s, pick.x);
+			t.valid = false;
+			t.flip = plane_side(sp.position, light.plane) < 0.0f;
+			t.specular.total = 0.0f;
+			#pragma unroll
+			for (int i = 0; i != 3; ++i) { pv[i] = to_shading_space(ltc, light.v[i], t.flip); pq[i] = to_cosine_space(ltc, light.v[i], t.flip); }
+			pv[3] = pq[3] = mk3(0.0f, 0.0f, 0.0f);
+			vc_d = clip_to_horizon<4>(light.count, pv, var.min_light_vertices);
+			if (vc_d != 0) vc_s = clip_to_horizon<4>(light.count, pq, var.min_light_vertices);
+			live = vc_d != 0;
+		}
+		__syncthreads();
+		// ---- (B), (C): prepare_techniques, shading_pass.frag.glsl:296-363
+		if (live) psa_prepare<4>(t.diffuse, vc_d, pv, false);
+		__syncthreads();
+		if (live && vc_s != 0) psa_prepare<4>(t.specular, vc_s, pq, false);
+		if (live) {
+			live = t.diffuse.total != 0.0f;
+			if (live) {
+				const float sw = ltc.albedo * t.specular.total;
+				const float3 da = mk3(fmaxf(sp.diffuse_albedo.x, 0.01f), fmaxf(sp.diffuse_albedo.y, 0.01f), fmaxf(sp.diffuse_albedo.z, 0.01f));
+				t.diffuse_weight = scale3(da, t.diffuse.total);
+				t.rcp_diffuse = 1.0f / t.diffuse.total;
+				t.rcp_specular = 1.0f / t.specular.total;
+				t.specular_weight = mk3(sw, sw, sw);
+				t.valid = true;
+			}
+		}
+		__syncthreads();
+		// ---- (D), (E): one sample per technique (SAMPLE_COUNT = 1), shading_pass.frag.glsl:365-372
+		uint32_t seed = pick.z;
+		float3 dir0 = mk3(0.0f, 0.0f, 0.0f), dir1 = dir0;
+		int techniques = 1;
+		if (live) {
+			const float u0 = noise_next(seed), u1 = noise_next(seed);
+			dir0 = psa_sample<4>(t.diffuse, u0, u1, false, false);
+		}
+		__syncthreads();
+		if (live && t.specular.total > 0.0f) {
+			const float u0 = noise_next(seed), u1 = noise_next(seed);
+			dir1 = cosine_to_shading_dir(ltc, psa_sample<4>(t.specular, u0, u1, false, false));
+			techniques = 2;
+		}
+		__syncthreads();
+		// ---- (F): densities, BRDF, MIS (shading_pass.frag.glsl:373-394); the rays are recorded for the trace kernel
+		float3 carry = mk3(0.0f, 0.0f, 0.0f);
+		if (live) {
+			for (int j = 0; j != techniques; ++j) {
+				RayRequest ray; bool side_visible; float3 if_occluded;
+				ray.dir = mk3(0.0f, 0.0f, 1.0f); ray.t_max = -1.0f; ray.if_visible = mk3(0.0f, 0.0f, 0.0f);
+				if (!technique_sample<3>(t, sp, ltc, light, var, j, j ? dir1 : dir0, f.mis_visibility_estimate, true, ray, side_visible, if_occluded)) continue;
+				if (!side_visible) { carry = add3(carry, if_occluded); continue; }
+				out.ray_a[(size_t) j * out.pixel_count + pixel] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t_max);
+				out.ray_b[(size_t) j * out.pixel_count + pixel] = make_float4(ray.if_visible.x, ray.if_visible.y, ray.if_visible.z, 1.0f);
+			}
+		}
+		if (shaded) {
+			out.group[pixel] = make_float4(carry.x, carry.y, carry.z, __uint_as_float(pick.y));
+			out.base[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
+		}
 	}
-	out.group[pixel] = make_float4(carry.x, carry.y, carry.z, __uint_as_float(pick.y));
-	out.base[pixel] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
 }
 
 }  // namespace RL_NS

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 				spilled += 8; nsp -= 8;
 			}
 			int next = -1;
+			float next_t = 0.0f;
 			#pragma unroll
 			for (int c = 0; c != 4; ++c) {
 				const uint32_t sel = 0x7604u | ((uint32_t) c << 4);
@@ -128,10 +129,14 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 				const bool leaf = hit && ref < 0, inner = hit && ref >= 0;
 				sm_lstack[lsp][tid] = ref;
 				lsp += leaf ? 1 : 0;
+				// of the inner children that are hit, the one the ray enters first is visited next (occluded rays end sooner);
+				// whichever of {next, ref} loses goes on the stack
 				const bool push = inner && next >= 0;
-				sm_nstack[nsp][tid] = next;
+				const bool closer = inner && (next < 0 || t0 < next_t);
+				sm_nstack[nsp][tid] = closer ? next : ref;
 				nsp += push ? 1 : 0;
-				next = inner ? ref : next;
+				next = closer ? ref : next;
+				next_t = closer ? t0 : next_t;
 			}
 			if (next < 0 && nsp == 0 && spilled != 0) {
 				spilled -= 8; nsp = 8;

@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "shade_fast.cuh"
 #include "trace4.cuh"
+#include "raster.cuh"
 #include "bvh_build.h"
 #include "clip_rotation_table.inc"
 #include <cstdio>
@@ -42,6 +43,8 @@ struct risltc_device_s {
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
 	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
+	uint32_t gbuffer_kind = 1;    // 1: triangle-parallel rasteriser (raster.cuh), 0: per-pixel BVH walk (gbuffer_kernel)
+	RasterBuffers raster = {};
 	uint32_t winner_threads = 256;   // CTA size of the phase-synchronous winner kernel (128, 256 or 512; 512 threads resident per SM)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
@@ -83,10 +86,15 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
 	CU(cudaMalloc(&d->px.ticket, sizeof(unsigned int)));
 	CU(cudaMemset(d->px.ticket, 0, sizeof(unsigned int)));
+	// rasteriser: item queue, {counter, ticket} in one 16-byte block
+	CU(cudaMalloc(&d->raster.items, (size_t) RL_RASTER_MAX_ITEMS * sizeof(RasterItem)));
+	CU(cudaMalloc(&d->raster.counter, 16));
+	d->raster.ticket = (unsigned int*) (d->raster.counter + 1);
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128) ? (uint32_t) t : 256u; }
+	if (const char* e = getenv("RISLTC_GBUFFER")) d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u;
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
@@ -96,7 +104,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 static void free_targets(risltc_device_t* d) {
 	cudaFree(d->px.pick); d->px.pick = nullptr;
 	cudaFree(d->px.visibility); cudaFree(d->px.origin); cudaFree(d->px.base); cudaFree(d->px.group);
-	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum);
+	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum); cudaFree(d->raster.zbuf); d->raster.zbuf = nullptr;
 	d->px.visibility = nullptr; d->px.origin = d->px.base = d->px.group = d->px.ray_a = d->px.ray_b = nullptr;
 	d->own_accum = nullptr; d->px.accum = nullptr;
 	d->ray_slots = d->group_slots = 0;
@@ -112,7 +120,7 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	cudaSetDevice(d->ordinal);
 	if (d->stream) cudaStreamSynchronize(d->stream);
 	free_targets(d); free_scene(d);
-	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters); cudaFree(d->px.ticket);
+	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters); cudaFree(d->px.ticket); cudaFree(d->raster.items); cudaFree(d->raster.counter);
 	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
@@ -295,6 +303,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMalloc(&d->px.origin, pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->px.base, pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->px.pick, pixels * sizeof(uint4)));
+	CU(cudaMalloc(&d->raster.zbuf, pixels * sizeof(unsigned long long)));
 	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
@@ -395,7 +404,16 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
 		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
 		CU(cudaEventRecord(fe[0], d->stream));
-		gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
+		if (d->gbuffer_kind == 1) {
+			// (1) every triangle finds its pixels and competes for them with atomicMin on {t, index} (raster.cuh)
+			CU(cudaMemsetAsync(d->raster.zbuf, 0xFF, (size_t) d->px.pixel_count * sizeof(unsigned long long), d->stream));
+			CU(cudaMemsetAsync(d->raster.counter, 0, 16, d->stream));
+			raster_setup_kernel<<<(d->view.triangle_count + 127) / 128, 128, 0, d->stream>>>(d->view, f, d->stripes, d->raster);
+			raster_tiles_kernel<<<d->sm_count * 8, 128, 0, d->stream>>>(d->view, f, d->stripes, d->raster);
+			raster_resolve_kernel<<<(d->px.pixel_count + 255) / 256, 256, 0, d->stream>>>(d->raster.zbuf, d->px.visibility, d->px.pixel_count);
+			d->launches += 2;
+		}
+		else gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
 		CU(cudaEventRecord(fe[1], d->stream));
 		if (launch_shade(d, grid, f)) return 1;
 		CU(cudaEventRecord(fe[2], d->stream));

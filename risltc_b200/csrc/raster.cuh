@@ -1,0 +1,239 @@
+// raster.cuh -- kernel (1), primary visibility (visibility_pass.vert/frag.glsl, raster state main.c:715-721,751-756),
+// second generation: TRIANGLE-parallel instead of ray-parallel.
+//
+// The visibility buffer is defined (oracle: closest_front_hit) as the lexicographic minimum of (t, triangle index) over
+// all front-facing triangles that the pixel-centre ray hits inside the depth range -- a definition that does not mention
+// a tree. gbuffer_kernel (kernels.cuh) evaluates it by walking the BVH per pixel (~42 node visits per ray, issue-bound);
+// here every triangle finds ITS pixels, as the reference's rasteriser does, and competes for them with a 64-bit
+// atomicMin on the key {bits(t) : index}:
+//   * the hit conditions u >= 0, v >= 0, u + v <= 1 (times det > 0) are LINEAR functions of the pixel coordinates because
+//     the ray direction is (pixel_to_ray * (px, py, 1)); the three functions, evaluated with generous margins, reject
+//     64x64 tiles, 8x4 blocks and single pixels that the triangle cannot cover (homogeneous rasterisation: no near-plane
+//     clipping, no division);
+//   * a pixel that survives runs EXACTLY the decision sequence of bvh_closest_front (tri_terms / tri_exact / depth clip with
+//     the same roundings), so the buffer is bit-identical to the ray-cast one;
+//   * raster_setup_kernel (one thread per triangle) culls back faces and triangles in front of the near plane, rasterises
+//     triangles with a small screen bounding box itself and queues the others as units of 64x64 pixels;
+//     raster_tiles_kernel (persistent CTAs, one unit at a time through a ticket) classifies a unit's 128 blocks of 8x4
+//     pixels one per lane and tests the pixels of the surviving blocks one per lane;
+//   * raster_resolve_kernel turns the keys into the u32 ids (index | emitter << 31, 0xFFFFFFFF = background).
+#pragma once
+#include "kernels.cuh"
+
+namespace RL_NS {
+
+#define RL_RASTER_SMALL 48u            // largest bounding box (pixels) that the setup thread rasterises itself
+#define RL_RASTER_TILE 64u             // a unit of raster_tiles_kernel is RL_RASTER_TILE^2 pixels
+#define RL_RASTER_MAX_ITEMS (1u << 18) // queued triangles (beyond that the setup thread rasterises whatever it has)
+
+struct __align__(16) RasterItem {
+	uint32_t tri, first_unit;      // slot in SceneView::tris; number of this triangle's first unit
+	uint16_t tx0, ty0, ntx, nty;   // its tiles: origin and counts, in units of RL_RASTER_TILE pixels
+	float fu[3], fv[3], fw[3];     // the three edge functions A px + B py + C (>= 0 inside, scaled by det > 0)
+	float slack[3];                // bound on their evaluation error anywhere on the screen
+};
+
+struct RasterBuffers {
+	unsigned long long* zbuf;        // [pixel_count] {bits(t) << 32 | index << 1 | emitter}, ~0 = background
+	RasterItem* items;
+	unsigned long long* counter;     // {items << 32 | units}, bumped by one atomic per queued triangle
+	unsigned int* ticket;            // next unit of raster_tiles_kernel
+};
+
+// slack[k]: 1e-4 of the magnitudes of the terms that function k is summed from, anywhere on the screen -- hundreds of ulps of
+// the fp32 evaluation (of the coefficients and of the sum), a fraction of a pixel in distance
+struct EdgeFunctions { float fu[3], fv[3], fw[3], slack[3]; };
+
+// Is the largest value of A px + B py + C over the pixel rectangle clearly negative?
+__device__ __forceinline__ bool edge_rejects(const float* e, float slack, float x0, float y0, float x1, float y1) {
+	return fmaf(e[0], e[0] > 0.0f ? x1 : x0, fmaf(e[1], e[1] > 0.0f ? y1 : y0, e[2])) < -slack;
+}
+__device__ __forceinline__ bool rect_rejected(const EdgeFunctions& ef, float x0, float y0, float x1, float y1) {
+	return edge_rejects(ef.fu, ef.slack[0], x0, y0, x1, y1) || edge_rejects(ef.fv, ef.slack[1], x0, y0, x1, y1) || edge_rejects(ef.fw, ef.slack[2], x0, y0, x1, y1);
+}
+__device__ __forceinline__ float edge_magnitude(float3 c0, float3 c1, float3 c2, float3 g, float w, float h) {
+	const float3 a = mk3(fabsf(g.x), fabsf(g.y), fabsf(g.z));
+	return dot3(mk3(fabsf(c0.x), fabsf(c0.y), fabsf(c0.z)), a) * w + dot3(mk3(fabsf(c1.x), fabsf(c1.y), fabsf(c1.z)), a) * h + dot3(mk3(fabsf(c2.x), fabsf(c2.y), fabsf(c2.z)), a);
+}
+
+// The per-frame quantities of the depth clip (rows 2 and 3 of world_to_projection applied to the ray) and the ray itself
+struct RasterFrame {
+	float3 o;
+	float zo, wo;
+};
+__device__ __forceinline__ RasterFrame raster_frame(const FrameUniforms& f) {
+	RasterFrame r;
+	r.o = mk3(f.camera[0], f.camera[1], f.camera[2]);
+	const float (*w2p)[4] = f.world_to_projection;
+	r.zo = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2p[2][0], r.o.x), __fmul_rn(w2p[2][1], r.o.y)), __fmul_rn(w2p[2][2], r.o.z)), w2p[2][3]);
+	r.wo = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2p[3][0], r.o.x), __fmul_rn(w2p[3][1], r.o.y)), __fmul_rn(w2p[3][2], r.o.z)), w2p[3][3]);
+	return r;
+}
+
+// One pixel against one triangle: the candidate test of bvh_closest_front (bvh.cuh), then the atomic competition.
+// (x, y) global pixel coordinates of a pixel this device owns; `pixel` its local index.
+__device__ __forceinline__ void raster_pixel(const FrameUniforms& f, const RasterFrame& rf, const BvhTri& tri, uint32_t x, uint32_t y, uint32_t pixel, unsigned long long* zbuf) {
+	const float3 d = primary_ray(f, x, y);
+	const TriTerms k = tri_terms(tri, rf.o, d);
+	if (!(k.det > 0.0f)) return;
+	const float r = approx_rcp(k.det);
+	const float ua = k.su * r, va = k.sv * r, ta = k.st * r;
+	if (ua < -RL_TRI_TINY || va < -RL_TRI_TINY || ua + va > 1.0f + RL_TRI_EPS || ta < -RL_TRI_TINY) return;
+	float t;
+	if (!tri_exact(k, t)) return;
+	if (!(t > 0.0f)) return;
+	const float (*w2p)[4] = f.world_to_projection;
+	const float zd = __fadd_rn(__fadd_rn(__fmul_rn(w2p[2][0], d.x), __fmul_rn(w2p[2][1], d.y)), __fmul_rn(w2p[2][2], d.z));
+	const float wd = __fadd_rn(__fadd_rn(__fmul_rn(w2p[3][0], d.x), __fmul_rn(w2p[3][1], d.y)), __fmul_rn(w2p[3][2], d.z));
+	const float zc = __fadd_rn(rf.zo, __fmul_rn(t, zd)), wc = __fadd_rn(rf.wo, __fmul_rn(t, wd));
+	if (!(zc >= 0.0f) || !(zc <= wc)) return;
+	const uint32_t id = __float_as_uint(tri.v0.w);
+	const unsigned long long key = ((unsigned long long) __float_as_uint(t) << 32) | (unsigned long long) ((id << 1) | (id >> 31));
+	if (key < zbuf[pixel]) atomicMin(&zbuf[pixel], key);   // the plain read can only be stale towards larger keys
+}
+
+__device__ __forceinline__ bool owned_row(const Stripes& st, uint32_t y, uint32_t& local_row) {
+	const uint32_t band = y / st.stripe_h;
+	local_row = (band / st.stripe_count) * st.stripe_h + (y - band * st.stripe_h);
+	return band % st.stripe_count == st.stripe_index;
+}
+
+__global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUniforms f, Stripes st, RasterBuffers rb) {
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= s.triangle_count) return;
+	const BvhTri tri = s.tris[slot];
+	const RasterFrame rf = raster_frame(f);
+	const float3 v0 = mk3(tri.v0.x, tri.v0.y, tri.v0.z), e1 = mk3(tri.e1.x, tri.e1.y, tri.e1.z), e2 = mk3(tri.e2.x, tri.e2.y, tri.e2.z);
+	const float3 sv = mk3(rf.o.x - v0.x, rf.o.y - v0.y, rf.o.z - v0.z);
+	// det = d . (e2 x e1), su = d . (e2 x s), sv = d . (s x e1): linear in the ray direction, hence in (px, py)
+	const float3 g_det = cross3(e2, e1), g_u = cross3(e2, sv), g_v = cross3(sv, e1);
+	// a ray through a point p of the triangle has d ~ p - o, so det ~ (p - o) . (e2 x e1) = -(sv . g_det) whatever p: the
+	// triangle is a back face (det <= 0) for every pixel when sv . g_det is clearly positive
+	const float facing = dot3(sv, g_det);
+	const float len_s = sqrtf(dot3(sv, sv)), len_n = sqrtf(dot3(g_det, g_det));
+	if (facing > 1.0e-4f * len_s * len_n) return;
+	const float3 c0 = mk3(f.pixel_to_ray[0][0], f.pixel_to_ray[1][0], f.pixel_to_ray[2][0]);
+	const float3 c1 = mk3(f.pixel_to_ray[0][1], f.pixel_to_ray[1][1], f.pixel_to_ray[2][1]);
+	const float3 c2 = mk3(f.pixel_to_ray[0][2], f.pixel_to_ray[1][2], f.pixel_to_ray[2][2]);
+	const float3 g_w = mk3(g_det.x - g_u.x - g_v.x, g_det.y - g_u.y - g_v.y, g_det.z - g_u.z - g_v.z);
+	EdgeFunctions ef;
+	ef.fu[0] = dot3(c0, g_u); ef.fu[1] = dot3(c1, g_u); ef.fu[2] = dot3(c2, g_u);
+	ef.fv[0] = dot3(c0, g_v); ef.fv[1] = dot3(c1, g_v); ef.fv[2] = dot3(c2, g_v);
+	ef.fw[0] = dot3(c0, g_w); ef.fw[1] = dot3(c1, g_w); ef.fw[2] = dot3(c2, g_w);
+	ef.slack[0] = 1.0e-4f * edge_magnitude(c0, c1, c2, g_u, (float) f.width, (float) f.height);
+	ef.slack[1] = 1.0e-4f * edge_magnitude(c0, c1, c2, g_v, (float) f.width, (float) f.height);
+	ef.slack[2] = ef.slack[0] + ef.slack[1] + 1.0e-4f * edge_magnitude(c0, c1, c2, g_det, (float) f.width, (float) f.height);
+	// ---- screen bounding box by projection; triangles that reach (half-way) towards the camera plane take the whole screen
+	const float (*w2p)[4] = f.world_to_projection;
+	float min_x = INFINITY, max_x = -INFINITY, min_y = INFINITY, max_y = -INFINITY, max_z = -INFINITY;
+	bool projectable = rf.zo < 0.0f;
+	#pragma unroll
+	for (int i = 0; i != 3; ++i) {
+		const float3 p = (i == 0) ? v0 : (i == 1) ? add3(v0, e1) : add3(v0, e2);
+		const float cx = w2p[0][0] * p.x + w2p[0][1] * p.y + w2p[0][2] * p.z + w2p[0][3];
+		const float cy = w2p[1][0] * p.x + w2p[1][1] * p.y + w2p[1][2] * p.z + w2p[1][3];
+		const float cz = w2p[2][0] * p.x + w2p[2][1] * p.y + w2p[2][2] * p.z + w2p[2][3];
+		const float cw = w2p[3][0] * p.x + w2p[3][1] * p.y + w2p[3][2] * p.z + w2p[3][3];
+		max_z = fmaxf(max_z, cz);
+		// z_clip rises from zo (< 0) at the camera plane to 0 at the near plane
+		if (!(cz > 0.5f * rf.zo) || !(cw > 0.0f)) projectable = false;
+		const float rw = 1.0f / cw;
+		const float px = (cx * rw + 1.0f) * (0.5f * (float) f.width) - 0.5f, py = (cy * rw + 1.0f) * (0.5f * (float) f.height) - 0.5f;
+		if (!(fabsf(px) < 1.0e7f) || !(fabsf(py) < 1.0e7f)) projectable = false;
+		min_x = fminf(min_x, px); max_x = fmaxf(max_x, px); min_y = fminf(min_y, py); max_y = fmaxf(max_y, py);
+	}
+	// entirely in front of the near plane (z_clip < 0 everywhere, with a margin relative to the camera's own -zo): never visible
+	if (max_z < 1.0e-3f * rf.zo) return;
+	int x0 = 0, y0 = 0, x1 = (int) f.width - 1, y1 = (int) f.height - 1;
+	if (projectable) {
+		x0 = max(x0, (int) floorf(min_x) - 1); x1 = min(x1, (int) ceilf(max_x) + 1);
+		y0 = max(y0, (int) floorf(min_y) - 1); y1 = min(y1, (int) ceilf(max_y) + 1);
+		if (x0 > x1 || y0 > y1) return;
+	}
+	if (rect_rejected(ef, (float) x0, (float) y0, (float) x1, (float) y1)) return;
+	const uint32_t w = (uint32_t) (x1 - x0 + 1), h = (uint32_t) (y1 - y0 + 1);
+	bool inline_raster = w * h <= RL_RASTER_SMALL;
+	if (!inline_raster) {
+		const uint32_t tx0 = (uint32_t) x0 / RL_RASTER_TILE, ty0 = (uint32_t) y0 / RL_RASTER_TILE;
+		const uint32_t ntx = (uint32_t) x1 / RL_RASTER_TILE - tx0 + 1u, nty = (uint32_t) y1 / RL_RASTER_TILE - ty0 + 1u;
+		const unsigned long long old = atomicAdd(rb.counter, (1ull << 32) + (unsigned long long) (ntx * nty));
+		const uint32_t index = (uint32_t) (old >> 32);
+		if (index < RL_RASTER_MAX_ITEMS) {
+			RasterItem it;
+			it.tri = slot; it.first_unit = (uint32_t) old;
+			it.tx0 = (uint16_t) tx0; it.ty0 = (uint16_t) ty0; it.ntx = (uint16_t) ntx; it.nty = (uint16_t) nty;
+			#pragma unroll
+			for (int i = 0; i != 3; ++i) { it.fu[i] = ef.fu[i]; it.fv[i] = ef.fv[i]; it.fw[i] = ef.fw[i]; it.slack[i] = ef.slack[i]; }
+			rb.items[index] = it;
+		}
+		else inline_raster = true;   // queue full: correct, only slow (its units are skipped by the tile kernel)
+	}
+	if (inline_raster) {
+		for (int y = y0; y <= y1; ++y) {
+			uint32_t row;
+			if (!owned_row(st, (uint32_t) y, row)) continue;
+			for (int x = x0; x <= x1; ++x) {
+				if (rect_rejected(ef, (float) x, (float) y, (float) x, (float) y)) continue;
+				raster_pixel(f, rf, tri, (uint32_t) x, (uint32_t) y, row * f.width + (uint32_t) x, rb.zbuf);
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUniforms f, Stripes st, RasterBuffers rb) {
+	__shared__ uint32_t sm_unit;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const unsigned long long counter = *rb.counter;
+	const uint32_t item_count = min((uint32_t) (counter >> 32), RL_RASTER_MAX_ITEMS), unit_count = (uint32_t) counter;
+	const RasterFrame rf = raster_frame(f);
+	while (true) {
+		__syncthreads();
+		if (threadIdx.x == 0) sm_unit = atomicAdd(rb.ticket, 1u);
+		__syncthreads();
+		const uint32_t unit = sm_unit;
+		if (unit >= unit_count) break;
+		// the item whose range of units contains `unit` (first_unit rises with the item index; dropped items leave a gap at the end)
+		uint32_t lo = 0, hi = item_count;
+		while (hi - lo > 1u) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (rb.items[mid].first_unit <= unit) lo = mid; else hi = mid;
+		}
+		if (item_count == 0u) continue;
+		const RasterItem it = rb.items[lo];
+		const uint32_t local = unit - it.first_unit;
+		if (local >= (uint32_t) it.ntx * it.nty) continue;   // a unit of a triangle that the setup thread kept for itself
+		const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_y = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
+		EdgeFunctions ef;
+		#pragma unroll
+		for (int i = 0; i != 3; ++i) { ef.fu[i] = it.fu[i]; ef.fv[i] = it.fv[i]; ef.fw[i] = it.fw[i]; ef.slack[i] = it.slack[i]; }
+		const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f, ty1 = (float) min(tile_y + RL_RASTER_TILE, f.height) - 1.0f;
+		if (rect_rejected(ef, (float) tile_x, (float) tile_y, tx1, ty1)) continue;
+		const BvhTri tri = s.tris[it.tri];
+		// 128 blocks of 8x4 pixels (8 across, 16 down), 32 per warp, classified one per lane
+		const uint32_t block = warp * 32u + lane;
+		const uint32_t bx = tile_x + (block & 7u) * 8u, by = tile_y + (block >> 3) * 4u;
+		uint32_t row0;
+		bool live = bx < f.width && by < f.height && owned_row(st, by, row0);
+		if (live) live = !rect_rejected(ef, (float) bx, (float) by, (float) min(bx + 7u, f.width - 1u), (float) min(by + 3u, f.height - 1u));
+		unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+		while (todo) {
+			const uint32_t b = (uint32_t) __ffs(todo) - 1u;
+			todo &= todo - 1u;
+			const uint32_t blk = warp * 32u + b;
+			const uint32_t x = tile_x + (blk & 7u) * 8u + (lane & 7u), y = tile_y + (blk >> 3) * 4u + (lane >> 3);
+			uint32_t row;
+			if (x < f.width && y < f.height && owned_row(st, y, row) && !rect_rejected(ef, (float) x, (float) y, (float) x, (float) y))
+				raster_pixel(f, rf, tri, x, y, row * f.width + x, rb.zbuf);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long long* zbuf, uint32_t* visibility, uint32_t pixel_count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= pixel_count) return;
+	const unsigned long long key = zbuf[i];
+	const uint32_t low = (uint32_t) key;
+	visibility[i] = (key == ~0ull) ? 0xFFFFFFFFu : ((low >> 1) | (low << 31));
+}
+
+}  // namespace RL_NS

@@ -43,7 +43,13 @@ struct risltc_device_s {
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
 	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
-	uint32_t gbuffer_kind = 1;    // 1: triangle-parallel rasteriser (raster.cuh), 0: per-pixel BVH walk (gbuffer_kernel)
+	// (1) has two bit-identical implementations: 1 = triangle-parallel rasteriser (raster.cuh; wins when few triangles cover
+	// the screen), 0 = per-pixel BVH walk (gbuffer_kernel; wins at high depth complexity). Unless RISLTC_GBUFFER pins one, the
+	// first two frames after a scene upload / resize run one each, timed with events, and the faster one is kept.
+	uint32_t gbuffer_kind = 1;
+	uint32_t gbuffer_tune = 0;    // 0: time the rasteriser next, 1: time the BVH walk next, 2: both in flight, 3: decided
+	cudaEvent_t tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
 	uint32_t winner_threads = 256;   // CTA size of the phase-synchronous winner kernel (128, 256 or 512; 512 threads resident per SM)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
@@ -94,7 +100,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128) ? (uint32_t) t : 256u; }
-	if (const char* e = getenv("RISLTC_GBUFFER")) d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u;
+	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
+	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
@@ -123,6 +130,7 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters); cudaFree(d->px.ticket); cudaFree(d->raster.items); cudaFree(d->raster.counter);
 	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
+	for (auto& ev : d->tune_ev) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
 	delete d;
 }
@@ -181,6 +189,7 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	CU(cudaMemcpy(d->tris, dt.data(), dt.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
 	d->view.positions = d->positions; d->view.normals_uv = d->normals_uv; d->view.material_indices = d->material_indices;
 	d->view.nodes = d->nodes; d->view.nodes4 = d->nodes4; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
+	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
 	return 0;
 }
 
@@ -307,6 +316,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
+	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
 	return allocate_ray_buffers(d);
 }
 
@@ -404,7 +414,21 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
 		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
 		CU(cudaEventRecord(fe[0], d->stream));
-		if (d->gbuffer_kind == 1) {
+		uint32_t kind = d->gbuffer_kind;
+		if (d->gbuffer_tune < 3) {
+			if (d->view.triangle_count > RL_RASTER_MAX_ITEMS) { d->gbuffer_kind = kind = 0; d->gbuffer_tune = 3; }   // beyond the rasteriser's queue
+			else if (d->gbuffer_tune == 2) {
+				float raster_ms = 0.0f, bvh_ms = 0.0f;
+				CU(cudaEventSynchronize(d->tune_ev[3]));
+				CU(cudaEventElapsedTime(&raster_ms, d->tune_ev[0], d->tune_ev[1]));
+				CU(cudaEventElapsedTime(&bvh_ms, d->tune_ev[2], d->tune_ev[3]));
+				d->gbuffer_kind = kind = (raster_ms <= bvh_ms) ? 1u : 0u;
+				d->gbuffer_tune = 3;
+			}
+			else kind = (d->gbuffer_tune == 0) ? 1u : 0u;
+		}
+		if (d->gbuffer_tune < 2) CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune], d->stream));
+		if (kind == 1) {
 			// (1) every triangle finds its pixels and competes for them with atomicMin on {t, index} (raster.cuh)
 			CU(cudaMemsetAsync(d->raster.zbuf, 0xFF, (size_t) d->px.pixel_count * sizeof(unsigned long long), d->stream));
 			CU(cudaMemsetAsync(d->raster.counter, 0, 16, d->stream));
@@ -414,6 +438,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			d->launches += 2;
 		}
 		else gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
+		if (d->gbuffer_tune < 2) { CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune + 1], d->stream)); d->gbuffer_tune++; }
 		CU(cudaEventRecord(fe[1], d->stream));
 		if (launch_shade(d, grid, f)) return 1;
 		CU(cudaEventRecord(fe[2], d->stream));

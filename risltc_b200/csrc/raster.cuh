@@ -24,7 +24,7 @@ namespace RL_NS {
 
 #define RL_RASTER_SMALL 48u            // largest bounding box (pixels) that the setup thread rasterises itself
 #define RL_RASTER_TILE 64u             // a unit of raster_tiles_kernel is RL_RASTER_TILE^2 pixels
-#define RL_RASTER_MAX_ITEMS (1u << 18) // queued triangles (beyond that the setup thread rasterises whatever it has)
+#define RL_RASTER_MAX_ITEMS (1u << 20) // queued triangles; scenes with more triangles than that use the BVH walk (api.cu)
 
 struct __align__(16) RasterItem {
 	uint32_t tri, first_unit;      // slot in SceneView::tris; number of this triangle's first unit

@@ -78,6 +78,18 @@ int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* var
 #define RISLTC_PRECISION_EXACT 1u
 int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 
+/* Two of the passes have two implementations each that produce bit-identical buffers (tests/test_gpu_frames.py):
+ *   visibility pass (visibility_pass.*.glsl): the triangle-parallel rasteriser or the per-pixel BVH walk; AUTO (default)
+ *     times both on the first two frames after upload_scene / resize and keeps the faster;
+ *   ray queries (shading_pass.frag.glsl:112-129): the 4-wide tree with 8-bit boxes (default) or the binary tree.
+ * This call pins them (the environment variables RISLTC_GBUFFER=raster|bvh and RISLTC_TRACE=4|2 do the same at create). */
+#define RISLTC_GBUFFER_BVH 0u
+#define RISLTC_GBUFFER_RASTER 1u
+#define RISLTC_GBUFFER_AUTO 2u
+#define RISLTC_SHADOW_BINARY 2u
+#define RISLTC_SHADOW_WIDE 4u
+int risltc_cuda_set_kernels(risltc_device_t* device, uint32_t gbuffer, uint32_t shadow);
+
 /* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
  * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index
  * (stripe_count = 1: the whole frame). Resets the accumulation buffer. */

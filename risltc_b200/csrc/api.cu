@@ -293,6 +293,17 @@ extern "C" int risltc_cuda_set_precision(risltc_device_t* d, uint32_t mode) {
 	return 0;
 }
 
+extern "C" int risltc_cuda_set_kernels(risltc_device_t* d, uint32_t gbuffer, uint32_t shadow) {
+	if (use(d)) return 1;
+	if (gbuffer > RISLTC_GBUFFER_AUTO || (shadow != RISLTC_SHADOW_BINARY && shadow != RISLTC_SHADOW_WIDE)) return fail("set_kernels: unknown kernel", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	d->gbuffer_pinned = gbuffer != RISLTC_GBUFFER_AUTO;
+	d->gbuffer_kind = (gbuffer == RISLTC_GBUFFER_BVH) ? 0u : 1u;
+	d->gbuffer_tune = d->gbuffer_pinned ? 3u : 0u;
+	d->trace_kind = shadow;
+	return 0;
+}
+
 extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t height, uint32_t stripe_height, uint32_t stripe_index, uint32_t stripe_count) {
 	if (use(d)) return 1;
 	if (width == 0 || height == 0 || stripe_count == 0 || stripe_index >= stripe_count || stripe_height == 0) return fail("resize: bad extent or stripe layout", nullptr);

@@ -70,9 +70,23 @@ __device__ __forceinline__ RasterFrame raster_frame(const FrameUniforms& f) {
 	return r;
 }
 
-// One pixel against one triangle: the candidate test of bvh_closest_front (bvh.cuh), then the atomic competition.
-// (x, y) global pixel coordinates of a pixel this device owns; `pixel` its local index.
-__device__ __forceinline__ void raster_pixel(const FrameUniforms& f, const RasterFrame& rf, const BvhTri& tri, uint32_t x, uint32_t y, uint32_t pixel, unsigned long long* zbuf) {
+// One pixel against one triangle. Cheap rejections first: (a) the three edge functions at the pixel, (b) EARLY Z -- along a
+// ray t = st / det where st = e2 . (s x e1) does not depend on the ray, so K / (Fu + Fv + Fw) estimates t for a few
+// instructions; a pixel whose estimate is clearly behind the key already in the buffer is skipped (the buffer is read without
+// synchronisation: a stale value is only larger, i.e. conservative). Whoever is left runs the candidate test of
+// bvh_closest_front (bvh.cuh) with its exact roundings and competes with atomicMin.
+// (x, y) global pixel coordinates of a pixel this device owns; `pixel` its local index; K = 0 disables early z.
+__device__ __forceinline__ void raster_pixel(const FrameUniforms& f, const RasterFrame& rf, const BvhTri& tri, const EdgeFunctions& ef, float K,
+	uint32_t x, uint32_t y, uint32_t pixel, unsigned long long* zbuf)
+{
+	const float fx = (float) x, fy = (float) y;
+	const float eu = fmaf(ef.fu[0], fx, fmaf(ef.fu[1], fy, ef.fu[2])), ev = fmaf(ef.fv[0], fx, fmaf(ef.fv[1], fy, ef.fv[2])), ew = fmaf(ef.fw[0], fx, fmaf(ef.fw[1], fy, ef.fw[2]));
+	if (eu < -ef.slack[0] || ev < -ef.slack[1] || ew < -ef.slack[2]) return;
+	const unsigned long long current = __ldcg(&zbuf[pixel]);   // from L2: a line cached in L1 would stay stale for the life of the CTA
+	const float current_t = __uint_as_float((uint32_t) (current >> 32));   // NaN while the pixel is background: never "behind"
+	const float det_estimate = eu + ev + ew;
+	// slack[2] is ~100x the rounding error of det_estimate: above 10 slack[2] the estimate of t is good to ~1e-3
+	if (det_estimate > 10.0f * ef.slack[2] && K * approx_rcp(det_estimate) * 0.998f > current_t) return;
 	const float3 d = primary_ray(f, x, y);
 	const TriTerms k = tri_terms(tri, rf.o, d);
 	if (!(k.det > 0.0f)) return;
@@ -89,7 +103,13 @@ __device__ __forceinline__ void raster_pixel(const FrameUniforms& f, const Raste
 	if (!(zc >= 0.0f) || !(zc <= wc)) return;
 	const uint32_t id = __float_as_uint(tri.v0.w);
 	const unsigned long long key = ((unsigned long long) __float_as_uint(t) << 32) | (unsigned long long) ((id << 1) | (id >> 31));
-	if (key < zbuf[pixel]) atomicMin(&zbuf[pixel], key);   // the plain read can only be stale towards larger keys
+	if (key < current) atomicMin(&zbuf[pixel], key);
+}
+// st = e2 . (s x e1) = -(s . (e2 x e1)) of the triangle, or 0 (no early z) where it is too small against its terms to be trusted
+__device__ __forceinline__ float early_z_constant(float3 sv, float3 g_det) {
+	const float facing = dot3(sv, g_det);
+	const float magnitude = fabsf(sv.x * g_det.x) + fabsf(sv.y * g_det.y) + fabsf(sv.z * g_det.z);
+	return (-facing > 1.0e-3f * magnitude) ? -facing : 0.0f;
 }
 
 __device__ __forceinline__ bool owned_row(const Stripes& st, uint32_t y, uint32_t& local_row) {
@@ -152,6 +172,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 	}
 	if (rect_rejected(ef, (float) x0, (float) y0, (float) x1, (float) y1)) return;
 	const uint32_t w = (uint32_t) (x1 - x0 + 1), h = (uint32_t) (y1 - y0 + 1);
+	const float K = early_z_constant(sv, g_det);
 	bool inline_raster = w * h <= RL_RASTER_SMALL;
 	if (!inline_raster) {
 		const uint32_t tx0 = (uint32_t) x0 / RL_RASTER_TILE, ty0 = (uint32_t) y0 / RL_RASTER_TILE;
@@ -173,8 +194,7 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 			uint32_t row;
 			if (!owned_row(st, (uint32_t) y, row)) continue;
 			for (int x = x0; x <= x1; ++x) {
-				if (rect_rejected(ef, (float) x, (float) y, (float) x, (float) y)) continue;
-				raster_pixel(f, rf, tri, (uint32_t) x, (uint32_t) y, row * f.width + (uint32_t) x, rb.zbuf);
+				raster_pixel(f, rf, tri, ef, K, (uint32_t) x, (uint32_t) y, row * f.width + (uint32_t) x, rb.zbuf);
 			}
 		}
 	}
@@ -209,6 +229,8 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 		const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f, ty1 = (float) min(tile_y + RL_RASTER_TILE, f.height) - 1.0f;
 		if (rect_rejected(ef, (float) tile_x, (float) tile_y, tx1, ty1)) continue;
 		const BvhTri tri = s.tris[it.tri];
+		const float K = early_z_constant(mk3(rf.o.x - tri.v0.x, rf.o.y - tri.v0.y, rf.o.z - tri.v0.z),
+			cross3(mk3(tri.e2.x, tri.e2.y, tri.e2.z), mk3(tri.e1.x, tri.e1.y, tri.e1.z)));
 		// 128 blocks of 8x4 pixels (8 across, 16 down), 32 per warp, classified one per lane
 		const uint32_t block = warp * 32u + lane;
 		const uint32_t bx = tile_x + (block & 7u) * 8u, by = tile_y + (block >> 3) * 4u;
@@ -222,8 +244,7 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 			const uint32_t blk = warp * 32u + b;
 			const uint32_t x = tile_x + (blk & 7u) * 8u + (lane & 7u), y = tile_y + (blk >> 3) * 4u + (lane >> 3);
 			uint32_t row;
-			if (x < f.width && y < f.height && owned_row(st, y, row) && !rect_rejected(ef, (float) x, (float) y, (float) x, (float) y))
-				raster_pixel(f, rf, tri, x, y, row * f.width + x, rb.zbuf);
+			if (x < f.width && y < f.height && owned_row(st, y, row)) raster_pixel(f, rf, tri, ef, K, x, y, row * f.width + x, rb.zbuf);
 		}
 	}
 }

@@ -121,6 +121,36 @@ def test_stripes_equal_whole_frame(device, ltc_tables, precision):
     assert np.array_equal(assembled.view(np.uint32), whole.view(np.uint32))
 
 
+def test_kernel_alternatives_are_bit_identical(device, ltc_tables):
+    """The rasteriser and the BVH walk (visibility), the 4-wide and the binary tree (shadow rays) are interchangeable:
+    visibility buffer and accumulated image must not differ in a single bit, whole frame or one stripe of three."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    _, rgba, rg = ltc_tables
+    W, H = 333, 190
+    scene = scenes.many_light_room(48, 120, seed=11, occluder_triangles=6000, width=W, height=H)
+    osc = orc.OracleScene(scene, rgba, rg)
+    cs = constants_bytes([orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0]) for f in range(3)])
+    _, ref_vis, _ = osc.render([orc.make_constants(scene, W, H, orc.frame_words(0)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0])], orc.variant())
+    try:
+        for stripes in ((8, 0, 1), (8, 1, 3)):
+            results = []
+            for gbuffer, shadow in (("raster", "wide"), ("bvh", "wide"), ("raster", "binary"), ("auto", "wide")):
+                setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records, stripes)
+                device.set_kernels(gbuffer, shadow)
+                device.render_frames(cs)
+                results.append((device.read_visibility().copy(), device.read_accum().copy()))
+            for vis, img in results[1:]:
+                assert np.array_equal(vis, results[0][0])
+                assert np.array_equal(img.view(np.uint32), results[0][1].view(np.uint32))
+            if stripes[2] == 1:
+                assert np.array_equal(results[0][0], ref_vis)
+            assert 0.2 < np.mean(results[0][0] != 0xFFFFFFFF) <= 1.0
+    finally:
+        device.set_kernels("auto", "wide")
+        device.resize(W, H, 8, 0, 1)
+
+
 def test_full_size_properties(device, ltc_tables):
     """BASELINE.json configs[1] at full size (1920x1080, 64 lights), checked through size-independent properties:
     determinism, accumulation = running mean of single frames, background / emitter pixels, fast vs exact agreement."""

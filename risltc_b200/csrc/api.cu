@@ -90,8 +90,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	d->sm_count = prop.multiProcessorCount;
 	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
-	CU(cudaMalloc(&d->px.ticket, sizeof(unsigned int)));
-	CU(cudaMemset(d->px.ticket, 0, sizeof(unsigned int)));
+	CU(cudaMalloc(&d->px.ticket, 4 * sizeof(unsigned int)));
+	CU(cudaMemset(d->px.ticket, 0, 4 * sizeof(unsigned int)));
 	// rasteriser: item queue, {counter, ticket} in one 16-byte block
 	CU(cudaMalloc(&d->raster.items, (size_t) RL_RASTER_MAX_ITEMS * sizeof(RasterItem)));
 	CU(cudaMalloc(&d->raster.counter, 16));
@@ -416,6 +416,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	if (d->view.light_stride4 != 3 + d->variant.max_light_vertices) return fail("render_frames: light buffer stride does not match the variant's max_light_vertices", nullptr);
 	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
 	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
+	CU(cudaMemsetAsync(d->px.ticket, 0, 4 * sizeof(unsigned int), d->stream));
 	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
 	d->timed_frames = frame_count;
 	CU(cudaEventRecord(d->ev[0], d->stream));

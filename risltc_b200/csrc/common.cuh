@@ -92,7 +92,7 @@ struct PixelBuffers {
 	uint4* pick;            // [pixels] RIS winner of the specialised path: light index, W (float bits), RNG state, unused
 	float4* accum;          // [pixels] RGBA32F running mean
 	unsigned long long* counters;   // [0] shaded pixels, [1] rays traced, [3] candidates
-	unsigned int* ticket;           // next unclaimed ray number of trace_kernel (zero between frames)
+	unsigned int* ticket;           // [0] next unclaimed ray of the trace kernel, [1] next tile of ris_ltc3_kernel, [2] of winner_kernel (zero between frames)
 	uint32_t pixel_count;
 };
 

@@ -192,9 +192,9 @@ extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint
 	if (!d->nodes || !d->nodes4) return fail("kat_trace: upload_scene first", nullptr);
 	if (kind != 2 && kind != 4) return fail("kat_trace: kind must be 2 or 4", nullptr);
 	DeviceArray<float> r; DeviceArray<uint32_t> h; DeviceArray<float4> og, ra, rb; DeviceArray<unsigned int> ticket;
-	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 1))
+	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 4))
 		return fail("kat_trace: allocation failed", nullptr);
-	CU(cudaMemset(ticket.p, 0, sizeof(unsigned int)));
+	CU(cudaMemset(ticket.p, 0, 4 * sizeof(unsigned int)));
 	PixelBuffers px = {};
 	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
 	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);

@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px
 template <bool TRACED>
 __global__ void __launch_bounds__(128) resolve_kernel(SceneView s, FrameUniforms f, Variant var, Stripes st, PixelBuffers out) {
 	uint32_t x, row, y;
-	if (TRACED && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *out.ticket = 0u;   // next frame's ray pool
+	if (TRACED && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3) out.ticket[threadIdx.x] = 0u;   // next frame's ray pool and tile tickets
 	if (!tile_pixel(f, st, x, row, y)) return;
 	const uint32_t pixel = row * f.width + x;
 	float4 o4 = out.origin[pixel], b4 = out.base[pixel];

@@ -156,14 +156,19 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 	if (SMEM) for (uint32_t i = threadIdx.x; i < 3u * staged; i += blockDim.x) sm_base[i] = __ldg(&s.lights_tri[i]);
 	__syncthreads();
 	const float4* table = SMEM ? sm_base : s.lights_tri;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t lt_mask = (1u << lane) - 1u;
 	float* ff = (float*) (sm_base + 3u * staged) + warp * RL_WARP_WORDS;   // [2][RL_CHUNK][32]
 	float* queue = ff + 2 * RL_CHUNK * 32;                                   // [RL_QUEUE][RL_ITEM_WORDS]
 	const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
 	uint32_t shaded = 0;
-	// a warp owns 8x4 pixel tiles; the warps of a CTA take neighbouring tiles
-	for (uint32_t tile = blockIdx.x * warps + warp; tile < tile_count; tile += gridDim.x * warps) {
+	// a warp owns 8x4 pixel tiles, handed out in order through a ticket: tiles differ a lot in cost (background, lights below
+	// the horizon, clipped polygons), and when the image is split over several devices a static share is only 2-3 tiles per warp
+	while (true) {
+		uint32_t tile = 0;
+		if (lane == 0) tile = atomicAdd(&out.ticket[1], 1u);
+		tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+		if (tile >= tile_count) break;
 		const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u);
 		const uint32_t row = (tile / tiles_x) * 4u + (lane >> 3);
 		const bool inside = x < f.width && row < st.owned_rows;
@@ -279,8 +284,14 @@ template <int RL_WIN_THREADS>
 __global__ void __launch_bounds__(RL_WIN_THREADS, 512 / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
 	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
-	// a warp owns 8x4 pixel tiles; all warps of the CTA run the same number of rounds (barriers inside)
-	for (uint32_t base = blockIdx.x * warps; base < tile_count; base += gridDim.x * warps) {
+	// a warp owns 8x4 pixel tiles; the CTA takes `warps` neighbouring tiles per round through a ticket (barriers inside)
+	__shared__ uint32_t sm_base;
+	while (true) {
+		__syncthreads();
+		if (threadIdx.x == 0) sm_base = atomicAdd(&out.ticket[2], warps);
+		__syncthreads();
+		const uint32_t base = sm_base;
+		if (base >= tile_count) break;
 		const uint32_t tile = base + warp;
 		const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u);
 		const uint32_t row = (tile / tiles_x) * 4u + (lane >> 3);

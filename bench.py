@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--stripe-height", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-stripes", type=int, default=0, help="profiling aid: render only stripe 0 of N on one GPU (the per-device share of an N-GPU run) and print its kernel times; not a bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -181,12 +182,24 @@ def main():
     # also used for the device-resident measurement, so both legs run the same kernels on the same data
     tmp = tempfile.TemporaryDirectory(prefix=f"risltc_bench_{rank}_")
     vks, tex, save = host.write_scene_files(wl["scene"], tmp.name, ltc_fits=wl["fits"])
-    app = host.Application(tmp.name, ordinal=local, stripe_height=args.stripe_height, stripe_index=rank, stripe_count=world)
+    app = host.Application(tmp.name, ordinal=local, stripe_height=args.stripe_height, stripe_index=rank if not args.emulate_stripes else 0,
+                           stripe_count=args.emulate_stripes or world)
     app.load(vks, tex, save, W, H)
     app.settings(light_sampling=api.LIGHT[kw.get("light_sampling", "reservoir")],
                  polygon_sampling_technique=api.POLY[kw.get("technique", "ltc_cp")], accum=1)
     dev = app.device()
     dev.set_precision(args.precision)
+    if args.emulate_stripes:
+        acc = np.zeros(4)
+        for i in range(args.warmup + args.steps):
+            app.reset(0)
+            app.render_frames(spp, upload_lights=False)
+            if i >= args.warmup:
+                acc += dev.last_kernel_ms()
+        print(json.dumps(dict(emulated_share=f"stripe 0 of {args.emulate_stripes}", workload=args.workload, per_step_ms=dict(zip(("gbuffer", "shade", "trace_resolve", "call"), (acc / args.steps).round(3).tolist())))))
+        app.close()
+        sys.stdout.flush()
+        os._exit(0)
     gat = multi.StripeGather(W, H, args.stripe_height, rank, world, device=f"cuda:{local}")
     multi.attach(dev, gat)
     stream = torch.cuda.ExternalStream(int(api.lib().risltc_cuda_stream(dev.h)), device=local)

@@ -90,6 +90,15 @@ int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 #define RISLTC_SHADOW_WIDE 4u
 int risltc_cuda_set_kernels(risltc_device_t* device, uint32_t gbuffer, uint32_t shadow);
 
+/* Frame overlap inside render_frames: consecutive frames alternate between two streams and two sets of per-frame buffers
+ * (only the accumulation stays ordered), which fills the tails of the persistent kernels. AUTO (default): on when the
+ * device renders a share of the image (stripe_count > 1), off for a whole frame so that last_kernel_ms() times each
+ * pass in isolation. The image does not depend on the mode. Environment: RISLTC_OVERLAP=0|1. */
+#define RISLTC_OVERLAP_OFF 0u
+#define RISLTC_OVERLAP_ON 1u
+#define RISLTC_OVERLAP_AUTO 2u
+int risltc_cuda_set_frame_overlap(risltc_device_t* device, uint32_t mode);
+
 /* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
  * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index
  * (stripe_count = 1: the whole frame). Resets the accumulation buffer. */

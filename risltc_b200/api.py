@@ -103,6 +103,9 @@ class Device:
     def set_kernels(self, gbuffer="auto", shadow="wide"):
         _check(lib().risltc_cuda_set_kernels(self.h, C.c_uint32({"bvh": 0, "raster": 1, "auto": 2}[gbuffer]), C.c_uint32({"binary": 2, "wide": 4}[shadow])))
 
+    def set_frame_overlap(self, mode="auto"):
+        _check(lib().risltc_cuda_set_frame_overlap(self.h, C.c_uint32({"off": 0, "on": 1, "auto": 2}[mode])))
+
     def resize(self, width, height, stripe_height=8, stripe_index=0, stripe_count=1):
         _check(lib().risltc_cuda_resize(self.h, C.c_uint32(width), C.c_uint32(height), C.c_uint32(stripe_height),
                                         C.c_uint32(stripe_index), C.c_uint32(stripe_count)))

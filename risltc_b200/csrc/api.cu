@@ -40,8 +40,19 @@ struct risltc_device_s {
 	PixelBuffers px = {};
 	float4* own_accum = nullptr;
 	uint32_t ray_slots = 0, group_slots = 0;
+	// Frame overlap: consecutive frames of a render_frames call alternate between two streams and two sets of per-frame
+	// buffers, so that the tail of one frame's persistent kernels (few warps left, SMs idling) is filled with the next
+	// frame's work; only the accumulation (resolve) of frame i waits for frame i - 1. On by default when the device renders
+	// a share of the image (stripe_count > 1: per-frame work is small against the tails), see risltc_cuda_set_frame_overlap.
+	PixelBuffers px2 = {};
+	RasterBuffers raster2 = {};
+	bool set2_ready = false, overlap = false, overlap_pinned = false;
+	cudaStream_t stream2 = nullptr;
+	cudaEvent_t ev_resolved[2] = { nullptr, nullptr }, ev_fork = nullptr, ev_join = nullptr;
+	uint32_t last_set = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
+	int trace_ctas_per_sm = 0;   // 0: as many as fit
 	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
 	// (1) has two bit-identical implementations: 1 = triangle-parallel rasteriser (raster.cuh; wins when few triangles cover
 	// the screen), 0 = per-pixel BVH walk (gbuffer_kernel; wins at high depth complexity). Unless RISLTC_GBUFFER pins one, the
@@ -83,6 +94,9 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	d->ordinal = cuda_ordinal;
 	CU(cudaSetDevice(cuda_ordinal));
 	CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&d->ev_resolved[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_resolved[1], cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
 	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
@@ -102,13 +116,24 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128) ? (uint32_t) t : 256u; }
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
 	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
+	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
+	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
 	*device = d;
 	return 0;
 }
 
+static void free_second_set(risltc_device_t* d) {
+	if (d->stream2) cudaStreamSynchronize(d->stream2);
+	cudaFree(d->px2.visibility); cudaFree(d->px2.origin); cudaFree(d->px2.base); cudaFree(d->px2.group); cudaFree(d->px2.ray_a); cudaFree(d->px2.ray_b);
+	cudaFree(d->px2.pick); cudaFree(d->px2.ticket); cudaFree(d->raster2.zbuf); cudaFree(d->raster2.items); cudaFree(d->raster2.counter);
+	d->px2 = PixelBuffers(); d->raster2 = RasterBuffers();
+	d->set2_ready = false; d->last_set = 0;
+}
+
 static void free_targets(risltc_device_t* d) {
+	free_second_set(d);
 	cudaFree(d->px.pick); d->px.pick = nullptr;
 	cudaFree(d->px.visibility); cudaFree(d->px.origin); cudaFree(d->px.base); cudaFree(d->px.group);
 	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum); cudaFree(d->raster.zbuf); d->raster.zbuf = nullptr;
@@ -132,6 +157,10 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->tune_ev) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
+	if (d->stream2) cudaStreamDestroy(d->stream2);
+	for (auto& ev : d->ev_resolved) if (ev) cudaEventDestroy(ev);
+	if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+	if (d->ev_join) cudaEventDestroy(d->ev_join);
 	delete d;
 }
 
@@ -259,6 +288,7 @@ static int allocate_ray_buffers(risltc_device_t* d) {
 	uint32_t groups = d->variant.light_samples, slots = groups * d->variant.sample_count * 2u;
 	size_t pixels = d->px.pixel_count;
 	if (!pixels) return 0;
+	if (groups > d->group_slots || slots > d->ray_slots) free_second_set(d);   // rebuilt on demand with the new sizes
 	if (groups > d->group_slots) {
 		cudaFree(d->px.group); d->px.group = nullptr;
 		CU(cudaMalloc(&d->px.group, pixels * groups * sizeof(float4)));
@@ -271,6 +301,40 @@ static int allocate_ray_buffers(risltc_device_t* d) {
 		d->ray_slots = slots;
 	}
 	CU(cudaMemsetAsync(d->px.ray_b, 0, pixels * d->ray_slots * sizeof(float4), d->stream));
+	return 0;
+}
+
+// The second set of per-frame buffers (same sizes as the first), created the first time two frames overlap
+static int ensure_second_set(risltc_device_t* d) {
+	if (d->set2_ready) return 0;
+	const size_t pixels = d->px.pixel_count;
+	PixelBuffers& p = d->px2;
+	p = PixelBuffers();
+	p.pixel_count = d->px.pixel_count; p.counters = d->px.counters; p.accum = d->px.accum;
+	CU(cudaMalloc(&p.visibility, pixels * sizeof(uint32_t)));
+	CU(cudaMalloc(&p.origin, pixels * sizeof(float4)));
+	CU(cudaMalloc(&p.base, pixels * sizeof(float4)));
+	CU(cudaMalloc(&p.pick, pixels * sizeof(uint4)));
+	CU(cudaMalloc(&p.group, pixels * d->group_slots * sizeof(float4)));
+	CU(cudaMalloc(&p.ray_a, pixels * d->ray_slots * sizeof(float4)));
+	CU(cudaMalloc(&p.ray_b, pixels * d->ray_slots * sizeof(float4)));
+	CU(cudaMalloc(&p.ticket, 4 * sizeof(unsigned int)));
+	CU(cudaMemset(p.ray_b, 0, pixels * d->ray_slots * sizeof(float4)));
+	CU(cudaMemset(p.ticket, 0, 4 * sizeof(unsigned int)));
+	CU(cudaMalloc(&d->raster2.zbuf, pixels * sizeof(unsigned long long)));
+	CU(cudaMalloc(&d->raster2.items, (size_t) RL_RASTER_MAX_ITEMS * sizeof(RasterItem)));
+	CU(cudaMalloc(&d->raster2.counter, 16));
+	d->raster2.ticket = (unsigned int*) (d->raster2.counter + 1);
+	d->set2_ready = true;
+	return 0;
+}
+
+extern "C" int risltc_cuda_set_frame_overlap(risltc_device_t* d, uint32_t mode) {
+	if (use(d)) return 1;
+	if (mode > RISLTC_OVERLAP_AUTO) return fail("set_frame_overlap: unknown mode", nullptr);
+	CU(cudaStreamSynchronize(d->stream));
+	d->overlap_pinned = mode != RISLTC_OVERLAP_AUTO;
+	d->overlap = (mode == RISLTC_OVERLAP_AUTO) ? d->stripes.stripe_count > 1 : mode == RISLTC_OVERLAP_ON;
 	return 0;
 }
 
@@ -328,6 +392,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
 	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
+	if (!d->overlap_pinned) d->overlap = stripe_count > 1;
 	return allocate_ray_buffers(d);
 }
 
@@ -369,7 +434,7 @@ static const uint32_t kMaxSmemLights = 2048;
 
 // (2): the specialised persistent kernel of shade_fast.cuh when the variant is the default estimator on triangle
 // lights and the device is in RISLTC_PRECISION_FAST, the generic kernel otherwise.
-static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f) {
+static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, const PixelBuffers& px, cudaStream_t stream) {
 	const Variant& v = d->variant;
 	const bool defer = deferred_rays(v);
 	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
@@ -384,26 +449,26 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f) {
 		const uint32_t tiles_x = (d->width + 7) / 8, tile_count = tiles_x * ((d->stripes.owned_rows + 3) / 4);
 		uint32_t ctas = (uint32_t) d->sm_count;
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
-		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
-		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		{
 			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles
 			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
 			uint32_t wctas = (512u / threads) * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (threads == 512) winner_kernel<512><<<wctas, 512, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
-			else if (threads == 256) winner_kernel<256><<<wctas, 256, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
-			else winner_kernel<128><<<wctas, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px, tiles_x, tile_count);
+			if (threads == 512) winner_kernel<512><<<wctas, 512, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else winner_kernel<128><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		}
 		d->launches += 1;
 	}
 	else if (v.max_light_vertices == 3) {
-		if (defer) shade_kernel<3, true><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
-		else shade_kernel<3, false><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+		if (defer) shade_kernel<3, true><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
+		else shade_kernel<3, false><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
 	}
 	else {
-		if (defer) shade_kernel<4, true><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
-		else shade_kernel<4, false><<<grid, 128, 0, d->stream>>>(d->view, f, v, d->stripes, d->px);
+		if (defer) shade_kernel<4, true><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
+		else shade_kernel<4, false><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
 	}
 	return 0;
 }
@@ -420,12 +485,28 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
 	d->timed_frames = frame_count;
 	CU(cudaEventRecord(d->ev[0], d->stream));
+	const bool overlap = d->overlap && frame_count >= 2;
+	if (overlap) {
+		if (ensure_second_set(d)) return 1;
+		d->px2.accum = d->px.accum;
+		CU(cudaEventRecord(d->ev_fork, d->stream));
+		CU(cudaStreamWaitEvent(d->stream2, d->ev_fork, 0));
+	}
+	uint32_t alternate = 0;
+	bool used_second = false;
 	for (uint32_t i = 0; i != frame_count; ++i) {
 		FrameUniforms f;
 		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
+		// while the G-buffer implementations are being timed the frames stay on one stream; afterwards they alternate
+		const uint32_t set = (overlap && d->gbuffer_tune == 3) ? (alternate++ & 1u) : 0u;
+		const PixelBuffers& px = set ? d->px2 : d->px;
+		const RasterBuffers& raster = set ? d->raster2 : d->raster;
+		cudaStream_t stream = set ? d->stream2 : d->stream;
+		used_second |= set != 0;
+		d->last_set = set;
 		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
-		CU(cudaEventRecord(fe[0], d->stream));
+		CU(cudaEventRecord(fe[0], stream));
 		uint32_t kind = d->gbuffer_kind;
 		if (d->gbuffer_tune < 3) {
 			if (d->view.triangle_count > RL_RASTER_MAX_ITEMS) { d->gbuffer_kind = kind = 0; d->gbuffer_tune = 3; }   // beyond the rasteriser's queue
@@ -439,32 +520,41 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			}
 			else kind = (d->gbuffer_tune == 0) ? 1u : 0u;
 		}
-		if (d->gbuffer_tune < 2) CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune], d->stream));
+		if (d->gbuffer_tune < 2) CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune], stream));
 		if (kind == 1) {
 			// (1) every triangle finds its pixels and competes for them with atomicMin on {t, index} (raster.cuh)
-			CU(cudaMemsetAsync(d->raster.zbuf, 0xFF, (size_t) d->px.pixel_count * sizeof(unsigned long long), d->stream));
-			CU(cudaMemsetAsync(d->raster.counter, 0, 16, d->stream));
-			raster_setup_kernel<<<(d->view.triangle_count + 127) / 128, 128, 0, d->stream>>>(d->view, f, d->stripes, d->raster);
-			raster_tiles_kernel<<<d->sm_count * 8, 128, 0, d->stream>>>(d->view, f, d->stripes, d->raster);
-			raster_resolve_kernel<<<(d->px.pixel_count + 255) / 256, 256, 0, d->stream>>>(d->raster.zbuf, d->px.visibility, d->px.pixel_count);
+			CU(cudaMemsetAsync(raster.zbuf, 0xFF, (size_t) px.pixel_count * sizeof(unsigned long long), stream));
+			CU(cudaMemsetAsync(raster.counter, 0, 16, stream));
+			raster_setup_kernel<<<(d->view.triangle_count + 127) / 128, 128, 0, stream>>>(d->view, f, d->stripes, raster);
+			raster_tiles_kernel<<<d->sm_count * 8, 128, 0, stream>>>(d->view, f, d->stripes, raster);
+			raster_resolve_kernel<<<(px.pixel_count + 255) / 256, 256, 0, stream>>>(raster.zbuf, px.visibility, px.pixel_count);
 			d->launches += 2;
 		}
-		else gbuffer_kernel<<<grid, 128, 0, d->stream>>>(d->view, f, d->stripes, d->px);
-		if (d->gbuffer_tune < 2) { CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune + 1], d->stream)); d->gbuffer_tune++; }
-		CU(cudaEventRecord(fe[1], d->stream));
-		if (launch_shade(d, grid, f)) return 1;
-		CU(cudaEventRecord(fe[2], d->stream));
-		if (d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant)) {
-			// (3) persistent any-hit traversal over all ray slots, (4) MIS sum + accumulation
-			const uint32_t ray_count = d->px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote, d->refill);
-			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, d->stream>>>(d->view, d->px, ray_count, d->tri_vote);
-			resolve_kernel<true><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
+		else gbuffer_kernel<<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);
+		if (d->gbuffer_tune < 2) { CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune + 1], stream)); d->gbuffer_tune++; }
+		CU(cudaEventRecord(fe[1], stream));
+		if (launch_shade(d, grid, f, px, stream)) return 1;
+		CU(cudaEventRecord(fe[2], stream));
+		const bool traced = d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant);
+		if (traced) {
+			// (3) persistent any-hit traversal over all ray slots
+			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
+			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < d->trace4_resident) ? d->trace_ctas_per_sm : d->trace4_resident;
+			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
+			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
 			d->launches += 1;
 		}
-		else resolve_kernel<false><<<grid, 128, 0, d->stream>>>(d->view, f, d->variant, d->stripes, d->px);
-		CU(cudaEventRecord(fe[3], d->stream));
+		// (4) MIS sum + accumulation: the running mean takes the frames in order, whichever stream they were rendered on
+		if (overlap && i != 0) CU(cudaStreamWaitEvent(stream, d->ev_resolved[(i - 1) & 1u], 0));
+		if (traced) resolve_kernel<true><<<grid, 128, 0, stream>>>(d->view, f, d->variant, d->stripes, px);
+		else resolve_kernel<false><<<grid, 128, 0, stream>>>(d->view, f, d->variant, d->stripes, px);
+		if (overlap) CU(cudaEventRecord(d->ev_resolved[i & 1u], stream));
+		CU(cudaEventRecord(fe[3], stream));
 		d->launches += 3;
+	}
+	if (used_second) {
+		CU(cudaEventRecord(d->ev_join, d->stream2));
+		CU(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
 	}
 	CU(cudaEventRecord(d->ev[4], d->stream));
 	CU(cudaGetLastError());
@@ -493,7 +583,7 @@ extern "C" int risltc_cuda_read_accum(risltc_device_t* d, float* rgba) {
 extern "C" int risltc_cuda_read_visibility(risltc_device_t* d, uint32_t* ids) {
 	if (use(d)) return 1;
 	if (!ids || !d->px.visibility) return fail("read_visibility: nothing to read", nullptr);
-	CU(cudaMemcpyAsync(ids, d->px.visibility, (size_t) d->px.pixel_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+	CU(cudaMemcpyAsync(ids, (d->last_set ? d->px2 : d->px).visibility, (size_t) d->px.pixel_count * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
 	CU(cudaStreamSynchronize(d->stream));
 	return 0;
 }

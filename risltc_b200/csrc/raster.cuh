@@ -112,10 +112,12 @@ __device__ __forceinline__ float early_z_constant(float3 sv, float3 g_det) {
 	return (-facing > 1.0e-3f * magnitude) ? -facing : 0.0f;
 }
 
-__device__ __forceinline__ bool owned_row(const Stripes& st, uint32_t y, uint32_t& local_row) {
+// Local index of the first row this device owns at or below the global row y (== owned_rows if there is none): the
+// rasteriser works in the device's own row space, so that a device that owns 1 / N of the rows does 1 / N of the work
+__device__ __forceinline__ uint32_t first_owned_local(const Stripes& st, uint32_t y) {
 	const uint32_t band = y / st.stripe_h;
-	local_row = (band / st.stripe_count) * st.stripe_h + (y - band * st.stripe_h);
-	return band % st.stripe_count == st.stripe_index;
+	const uint32_t before = band > st.stripe_index ? (band - st.stripe_index + st.stripe_count - 1u) / st.stripe_count : 0u;   // owned bands above
+	return before * st.stripe_h + ((band % st.stripe_count == st.stripe_index) ? y - band * st.stripe_h : 0u);
 }
 
 __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUniforms f, Stripes st, RasterBuffers rb) {
@@ -171,12 +173,15 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 		if (x0 > x1 || y0 > y1) return;
 	}
 	if (rect_rejected(ef, (float) x0, (float) y0, (float) x1, (float) y1)) return;
-	const uint32_t w = (uint32_t) (x1 - x0 + 1), h = (uint32_t) (y1 - y0 + 1);
+	// the rows of the box that this device owns, as a range of its local rows
+	const uint32_t l0 = first_owned_local(st, (uint32_t) y0), l_end = min(first_owned_local(st, (uint32_t) y1 + 1u), st.owned_rows);
+	if (l0 >= l_end) return;
+	const uint32_t w = (uint32_t) (x1 - x0 + 1), h = l_end - l0;
 	const float K = early_z_constant(sv, g_det);
 	bool inline_raster = w * h <= RL_RASTER_SMALL;
 	if (!inline_raster) {
-		const uint32_t tx0 = (uint32_t) x0 / RL_RASTER_TILE, ty0 = (uint32_t) y0 / RL_RASTER_TILE;
-		const uint32_t ntx = (uint32_t) x1 / RL_RASTER_TILE - tx0 + 1u, nty = (uint32_t) y1 / RL_RASTER_TILE - ty0 + 1u;
+		const uint32_t tx0 = (uint32_t) x0 / RL_RASTER_TILE, ty0 = l0 / RL_RASTER_TILE;
+		const uint32_t ntx = (uint32_t) x1 / RL_RASTER_TILE - tx0 + 1u, nty = (l_end - 1u) / RL_RASTER_TILE - ty0 + 1u;
 		const unsigned long long old = atomicAdd(rb.counter, (1ull << 32) + (unsigned long long) (ntx * nty));
 		const uint32_t index = (uint32_t) (old >> 32);
 		if (index < RL_RASTER_MAX_ITEMS) {
@@ -190,12 +195,9 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 		else inline_raster = true;   // queue full: correct, only slow (its units are skipped by the tile kernel)
 	}
 	if (inline_raster) {
-		for (int y = y0; y <= y1; ++y) {
-			uint32_t row;
-			if (!owned_row(st, (uint32_t) y, row)) continue;
-			for (int x = x0; x <= x1; ++x) {
-				raster_pixel(f, rf, tri, ef, K, (uint32_t) x, (uint32_t) y, row * f.width + (uint32_t) x, rb.zbuf);
-			}
+		for (uint32_t row = l0; row != l_end; ++row) {
+			const uint32_t y = st.global_row(row);
+			for (int x = x0; x <= x1; ++x) raster_pixel(f, rf, tri, ef, K, (uint32_t) x, y, row * f.width + (uint32_t) x, rb.zbuf);
 		}
 	}
 }
@@ -222,29 +224,29 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 		const RasterItem it = rb.items[lo];
 		const uint32_t local = unit - it.first_unit;
 		if (local >= (uint32_t) it.ntx * it.nty) continue;   // a unit of a triangle that the setup thread kept for itself
-		const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_y = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
+		// tiles are RL_RASTER_TILE pixels wide and RL_RASTER_TILE of this device's LOCAL rows high
+		const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_row = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
 		EdgeFunctions ef;
 		#pragma unroll
 		for (int i = 0; i != 3; ++i) { ef.fu[i] = it.fu[i]; ef.fv[i] = it.fv[i]; ef.fw[i] = it.fw[i]; ef.slack[i] = it.slack[i]; }
-		const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f, ty1 = (float) min(tile_y + RL_RASTER_TILE, f.height) - 1.0f;
-		if (rect_rejected(ef, (float) tile_x, (float) tile_y, tx1, ty1)) continue;
+		const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f;
+		const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + RL_RASTER_TILE, st.owned_rows) - 1u);
+		if (rect_rejected(ef, (float) tile_x, ty0, tx1, ty1)) continue;
 		const BvhTri tri = s.tris[it.tri];
 		const float K = early_z_constant(mk3(rf.o.x - tri.v0.x, rf.o.y - tri.v0.y, rf.o.z - tri.v0.z),
 			cross3(mk3(tri.e2.x, tri.e2.y, tri.e2.z), mk3(tri.e1.x, tri.e1.y, tri.e1.z)));
 		// 128 blocks of 8x4 pixels (8 across, 16 down), 32 per warp, classified one per lane
 		const uint32_t block = warp * 32u + lane;
-		const uint32_t bx = tile_x + (block & 7u) * 8u, by = tile_y + (block >> 3) * 4u;
-		uint32_t row0;
-		bool live = bx < f.width && by < f.height && owned_row(st, by, row0);
-		if (live) live = !rect_rejected(ef, (float) bx, (float) by, (float) min(bx + 7u, f.width - 1u), (float) min(by + 3u, f.height - 1u));
+		const uint32_t bx = tile_x + (block & 7u) * 8u, brow = tile_row + (block >> 3) * 4u;
+		bool live = bx < f.width && brow < st.owned_rows;
+		if (live) live = !rect_rejected(ef, (float) bx, (float) st.global_row(brow), (float) min(bx + 7u, f.width - 1u), (float) st.global_row(min(brow + 3u, st.owned_rows - 1u)));
 		unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
 		while (todo) {
 			const uint32_t b = (uint32_t) __ffs(todo) - 1u;
 			todo &= todo - 1u;
 			const uint32_t blk = warp * 32u + b;
-			const uint32_t x = tile_x + (blk & 7u) * 8u + (lane & 7u), y = tile_y + (blk >> 3) * 4u + (lane >> 3);
-			uint32_t row;
-			if (x < f.width && y < f.height && owned_row(st, y, row)) raster_pixel(f, rf, tri, ef, K, x, y, row * f.width + x, rb.zbuf);
+			const uint32_t x = tile_x + (blk & 7u) * 8u + (lane & 7u), row = tile_row + (blk >> 3) * 4u + (lane >> 3);
+			if (x < f.width && row < st.owned_rows) raster_pixel(f, rf, tri, ef, K, x, st.global_row(row), row * f.width + x, rb.zbuf);
 		}
 	}
 }

@@ -146,8 +146,19 @@ def test_kernel_alternatives_are_bit_identical(device, ltc_tables):
             if stripes[2] == 1:
                 assert np.array_equal(results[0][0], ref_vis)
             assert 0.2 < np.mean(results[0][0] != 0xFFFFFFFF) <= 1.0
+        # frame overlap (two streams, two sets of per-frame buffers) must not change a bit either, with 7 frames in flight
+        cs7 = constants_bytes([orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0]) for f in range(7)])
+        images = []
+        for mode in ("off", "on"):
+            setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records, (8, 1, 3))
+            device.set_frame_overlap(mode)
+            device.render_frames(cs7)
+            images.append((device.read_visibility().copy(), device.read_accum().copy()))
+        assert np.array_equal(images[0][0], images[1][0])
+        assert np.array_equal(images[0][1].view(np.uint32), images[1][1].view(np.uint32))
     finally:
         device.set_kernels("auto", "wide")
+        device.set_frame_overlap("auto")
         device.resize(W, H, 8, 0, 1)
 
 

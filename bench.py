@@ -33,6 +33,17 @@ sys.path.insert(0, str(ROOT))
 
 import numpy as np  # noqa: E402
 
+# The contract is ONE JSON line on stdout. The C host layer (like the reference's main.c) printf()s progress messages, so
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+_STDOUT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    os.write(_STDOUT_FD, (json.dumps(obj) + "\n").encode())
+
+
 WORKLOADS = {
     # name: (description, lights, boxes, occluder triangles, W, H, spp, light vertices)
     "c1": ("single quad area light over a diffuse plane, 640x360, 1 spp, polygon_sampling only", 1, 0, 0, 640, 360, 1, 4),
@@ -44,6 +55,9 @@ WORKLOADS = {
 FLOP_PER_CANDIDATE = {3: 303.0, 4: 394.0}
 FLOP_PER_SHADED_PIXEL = 1835.0 + 535.0 + 8.0
 FP32_LANES_PER_SM, SM_COUNT, SM_MAX_MHZ = 128, 148, 1965.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of ris_ltc3_kernel (the dominant kernel of the shading pass)
+# from an `ncu --set full` capture of this bench (profiles/r1_ncu_final_kernels.txt); far below any HBM bound, as the model says
+RIS_KERNEL_DRAM_BYTES = {"c2": 8.5e6}
 
 
 def make_workload(name):
@@ -145,7 +159,7 @@ def run_reference_arm(args, rank):
                 cpu_baseline=dict(value=value, unit="Gsamples/s", cores=cores, kind=kind,
                                   sample=f"{frames} frame(s) of {wl['spp']} at {wl['W']}x{wl['H']} per step, all host threads (OpenMP over rows)"),
                 e2e=dict(value=value, unit="Gsamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -196,7 +210,7 @@ def main():
             app.render_frames(spp, upload_lights=False)
             if i >= args.warmup:
                 acc += dev.last_kernel_ms()
-        print(json.dumps(dict(emulated_share=f"stripe 0 of {args.emulate_stripes}", workload=args.workload, per_step_ms=dict(zip(("gbuffer", "shade", "trace_resolve", "call"), (acc / args.steps).round(3).tolist())))))
+        emit((dict(emulated_share=f"stripe 0 of {args.emulate_stripes}", workload=args.workload, per_step_ms=dict(zip(("gbuffer", "shade", "trace_resolve", "call"), (acc / args.steps).round(3).tolist())))))
         app.close()
         sys.stdout.flush()
         os._exit(0)
@@ -248,8 +262,19 @@ def main():
     barrier()
     clock_info = clocks.stop() if clocks else None
     ms = start.elapsed_time(end)
+    breakdown_note = "CUDA events around each pass inside the timed region"
+    launches = dev.counters()["launches"] - launches0
+    if world >= 4:
+        # a device that renders a small share overlaps consecutive frames on two streams (risltc_cuda_set_frame_overlap), so the
+        # per-pass event intervals of the timed region overlap each other: take the breakdown from two extra, serial steps
+        dev.set_frame_overlap("off")
+        kernel_ms[:] = 0.0
+        for _ in range(2):
+            resident_step(True)
+        kernel_ms[:] *= args.steps / 2.0
+        dev.set_frame_overlap("auto")
+        breakdown_note = "frames overlap in the timed region; per-pass times from two extra serial steps"
     counters = dev.counters()
-    launches = counters["launches"] - launches0
     t = torch.tensor([ms, float(counters["shaded_pixels"]), float(counters["candidates"]), float(counters["shadow_rays"]), float(launches)] + list(kernel_ms),
                      dtype=torch.float64, device=f"cuda:{local}")
     tmax = t.clone()
@@ -285,13 +310,13 @@ def main():
         achieved = flop_per_step / (shade_ms_per_step * 1e-3) / 1e12 if shade_ms_per_step > 0 else 0.0
         frames_per_step = spp
         roofline = dict(bound="fp32", kernel="shade_kernel (fused RIS + shading)", achieved=achieved, peak=peak, unit="TFLOP/s",
-                        frac=achieved / peak if peak else None, traffic=None,
+                        frac=achieved / peak if peak else None, traffic=RIS_KERNEL_DRAM_BYTES.get(args.workload),
                         peak_source=("2*128 lanes*148 SMs*SM clock sampled by nvidia-smi during the timed region" if clock_info and clock_info["sm_mhz"]
                                      else "2*128 lanes*148 SMs*1965 MHz (nominal max clock; nvidia-smi sampling unavailable)"),
                         flop_per_launch=flop_per_step / frames_per_step / world, ms_per_launch=shade_ms_per_step / frames_per_step,
                         flop_model="303 flop per RIS candidate (V=3) + 2378 per shaded pixel-sample, SURVEY.md 8d")
         kernels = dict(gbuffer_ms=float(tmax[5]) / args.steps, shade_ms=float(tmax[6]) / args.steps, resolve_ms=float(tmax[7]) / args.steps,
-                       render_call_ms=float(tmax[8]) / args.steps, shadow_rays_per_step=float(t[3]), shaded_pixel_samples_per_step=shaded)
+                       render_call_ms=float(tmax[8]) / args.steps, shadow_rays_per_step=float(t[3]), shaded_pixel_samples_per_step=shaded, note=breakdown_note)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             dt, samples, kind, cores = cpu_reference_run(wl, 1)
@@ -312,7 +337,7 @@ def main():
                     gpu_launches=int(float(t[4])), roofline=roofline, kernels=kernels, pixel_samples_per_s=W * H * spp * args.steps / (ms_max * 1e-3))
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     barrier()
     # tear down in dependency order: the device object references the gather slab; the library's own CUDA runtime
     # instance must not outlive torch's tensors at interpreter exit

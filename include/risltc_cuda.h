@@ -92,8 +92,8 @@ int risltc_cuda_set_kernels(risltc_device_t* device, uint32_t gbuffer, uint32_t 
 
 /* Frame overlap inside render_frames: consecutive frames alternate between two streams and two sets of per-frame buffers
  * (only the accumulation stays ordered), which fills the tails of the persistent kernels. AUTO (default): on when the
- * device renders a share of the image (stripe_count > 1), off for a whole frame so that last_kernel_ms() times each
- * pass in isolation. The image does not depend on the mode. Environment: RISLTC_OVERLAP=0|1. */
+ * device renders a small share of the image (stripe_count >= 4 and at most 1.2 M pixels, where it measures faster), off
+ * otherwise -- then last_kernel_ms() also times each pass in isolation. The image does not depend on the mode. Environment: RISLTC_OVERLAP=0|1. */
 #define RISLTC_OVERLAP_OFF 0u
 #define RISLTC_OVERLAP_ON 1u
 #define RISLTC_OVERLAP_AUTO 2u

@@ -43,7 +43,7 @@ struct risltc_device_s {
 	// Frame overlap: consecutive frames of a render_frames call alternate between two streams and two sets of per-frame
 	// buffers, so that the tail of one frame's persistent kernels (few warps left, SMs idling) is filled with the next
 	// frame's work; only the accumulation (resolve) of frame i waits for frame i - 1. On by default when the device renders
-	// a share of the image (stripe_count > 1: per-frame work is small against the tails), see risltc_cuda_set_frame_overlap.
+	// a small share of the image (overlap_pays below), see risltc_cuda_set_frame_overlap.
 	PixelBuffers px2 = {};
 	RasterBuffers raster2 = {};
 	bool set2_ready = false, overlap = false, overlap_pinned = false;
@@ -62,6 +62,7 @@ struct risltc_device_s {
 	cudaEvent_t tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
+	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (512: 117 registers, 768: 80, 1024: 64 with spills)
 	uint32_t winner_threads = 256;   // CTA size of the phase-synchronous winner kernel (128, 256 or 512; 512 threads resident per SM)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
@@ -113,6 +114,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
+	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { int t = atoi(e); d->winner_resident = (t == 512 || t == 1024) ? (uint32_t) t : 768u; if (t != 512) d->winner_threads = 256; }
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128) ? (uint32_t) t : 256u; }
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
 	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
@@ -304,6 +306,11 @@ static int allocate_ray_buffers(risltc_device_t* d) {
 	return 0;
 }
 
+// Measured on B200 (bench.py --emulate-stripes, C2 and C3): overlapping frames wins 9-19 % when a device renders a quarter or
+// less of a frame and at most ~1 M pixels (the tails of the persistent kernels are then a fifth of a frame's time), and
+// loses 2-6 % on larger shares, where two frames' kernels mostly get in each other's way
+static bool overlap_pays(const risltc_device_t* d) { return d->stripes.stripe_count >= 4 && d->px.pixel_count <= 1200000u; }
+
 // The second set of per-frame buffers (same sizes as the first), created the first time two frames overlap
 static int ensure_second_set(risltc_device_t* d) {
 	if (d->set2_ready) return 0;
@@ -334,7 +341,7 @@ extern "C" int risltc_cuda_set_frame_overlap(risltc_device_t* d, uint32_t mode) 
 	if (mode > RISLTC_OVERLAP_AUTO) return fail("set_frame_overlap: unknown mode", nullptr);
 	CU(cudaStreamSynchronize(d->stream));
 	d->overlap_pinned = mode != RISLTC_OVERLAP_AUTO;
-	d->overlap = (mode == RISLTC_OVERLAP_AUTO) ? d->stripes.stripe_count > 1 : mode == RISLTC_OVERLAP_ON;
+	d->overlap = (mode == RISLTC_OVERLAP_AUTO) ? overlap_pays(d) : mode == RISLTC_OVERLAP_ON;
 	return 0;
 }
 
@@ -392,7 +399,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
 	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
-	if (!d->overlap_pinned) d->overlap = stripe_count > 1;
+	if (!d->overlap_pinned) d->overlap = overlap_pays(d);
 	return allocate_ray_buffers(d);
 }
 
@@ -454,11 +461,13 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		{
 			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles
 			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
-			uint32_t wctas = (512u / threads) * (uint32_t) d->sm_count;
+			uint32_t wctas = (d->winner_resident / threads) * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (threads == 512) winner_kernel<512><<<wctas, 512, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 256) winner_kernel<256><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else winner_kernel<128><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			if (d->winner_resident == 768) winner_kernel<256, 768><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (d->winner_resident == 1024) winner_kernel<256, 1024><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 512) winner_kernel<512, 512><<<wctas, 512, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else winner_kernel<128, 512><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		}
 		d->launches += 1;
 	}

@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 // light, both clipped polygons; (B) PSA preparation of the diffuse polygon; (C) of the specular polygon (the same code,
 // still cached); (D) diffuse sample; (E) specular sample (same code); (F) densities, BRDF, MIS weights, ray records.
 // The draws keep the reference's order (diffuse pair, then specular pair only if its solid angle is positive).
-template <int RL_WIN_THREADS>
-__global__ void __launch_bounds__(RL_WIN_THREADS, 512 / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+template <int RL_WIN_THREADS, int RL_WIN_RESIDENT_THREADS>
+__global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
 	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
 	// a warp owns 8x4 pixel tiles; the CTA takes `warps` neighbouring tiles per round through a ticket (barriers inside)

@@ -159,6 +159,11 @@ int risltc_cuda_kat_trace(risltc_device_t* device, const float* rays, uint32_t* 
  * stand for: [0] inversesqrt vs 1 / sqrt over every float of its fast range, [1] unorm16 vs x / 65535 for 0..65535,
  * [2] inversesqrt over every other bit pattern. All three must be 0. */
 int risltc_cuda_kat_exact_math(risltc_device_t* device, uint64_t mismatches[3]);
+/* Host-only (no device): builds the acceleration structures of upload_scene for `triangle_count` triangles (9 floats each)
+ * and checks their invariants. report = {triangles not in exactly one leaf slot, vertices outside their (padded) leaf box,
+ * violations of the 4-wide tree (a leaf / node not referenced exactly once, a quantised box that does not contain the
+ * binary tree's box), binary nodes, 4-wide nodes, depth << 32 | children per 4-wide node x 100}. The first three must be 0. */
+int risltc_cuda_check_bvh(const float* vertices, uint64_t triangle_count, uint32_t max_leaf, uint64_t report[6]);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def check_bvh(vertices, max_leaf=2):
+    """Host-only check of the BVH builders (binary tree and its 4-wide, 8-bit collapse); vertices [T, 3, 3] float32."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 9)
+    report = (C.c_uint64 * 6)()
+    _check(lib().risltc_cuda_check_bvh(_p(v), C.c_uint64(v.shape[0]), C.c_uint32(max_leaf), report))
+    r = [int(x) for x in report]
+    return dict(bad_order=r[0], bad_binary=r[1], bad_wide=r[2], binary_nodes=r[3], wide_nodes=r[4], depth=r[5] >> 32, children_per_node=(r[5] & 0xFFFFFFFF) / 100.0)
+
+
 class Device:
     """One risltc_device_t: one CUDA device, one stream, one image stripe set."""
 

@@ -11,6 +11,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <utility>
 
 using namespace exact;
 
@@ -622,6 +624,67 @@ extern "C" int risltc_cuda_counters(risltc_device_t* d, uint64_t counters[4]) {
 	CU(cudaMemcpyAsync(h, d->px.counters, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
 	CU(cudaStreamSynchronize(d->stream));
 	counters[0] = h[0]; counters[1] = h[1]; counters[2] = d->launches; counters[3] = h[3];
+	return 0;
+}
+
+// Host-only self check of the acceleration structures (no device needed): builds the binary tree and its 4-wide, 8-bit
+// collapse for a triangle soup and verifies the invariants the traversal kernels rely on.
+extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t max_leaf, uint64_t report[6]) {
+	if (!vertices || T == 0 || !report) return fail("check_bvh: no triangles", nullptr);
+	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
+	build_bvh(vertices, T, nodes, order, max_leaf);
+	std::vector<Qbvh4NodeHost> n4;
+	const uint32_t depth = build_qbvh4(nodes, n4);
+	// every triangle appears in exactly one leaf slot
+	std::vector<uint32_t> seen(T, 0);
+	for (uint32_t t : order) if (t < T) seen[t]++;
+	uint64_t bad_order = 0;
+	for (uint64_t t = 0; t != T; ++t) bad_order += seen[t] != 1;
+	// leaf boxes of the binary tree by reference
+	struct LeafBox { float lo[3], hi[3]; };
+	std::vector<std::pair<int, LeafBox>> leaves;
+	uint64_t bad_binary = 0;
+	auto check_leaf = [&](int ref, const float* lo, const float* hi) {
+		const uint32_t r = ~(uint32_t) ref, first = r >> 4, count = (r & 15u) + 1u;
+		for (uint32_t s2 = first; s2 != first + count; ++s2)
+			for (int v = 0; v != 3; ++v)
+				for (int k = 0; k != 3; ++k) {
+					const float x = vertices[9 * (size_t) order[s2] + 3 * v + k];
+					if (!(x >= lo[k] && x <= hi[k])) ++bad_binary;
+				}
+		LeafBox b; memcpy(b.lo, lo, 12); memcpy(b.hi, hi, 12);
+		leaves.push_back({ ref, b });
+	};
+	for (const BvhNodeHost& n : nodes) {
+		if (n.left < 0) check_leaf(n.left, n.left_lo, n.left_hi);
+		if (n.right < 0 && n.right_lo[0] <= n.right_hi[0]) check_leaf(n.right, n.right_lo, n.right_hi);
+	}
+	std::sort(leaves.begin(), leaves.end(), [](const std::pair<int, LeafBox>& a, const std::pair<int, LeafBox>& b) { return a.first < b.first; });
+	// 4-wide tree: every leaf reference appears once with a quantised box that contains the binary tree's box; every inner node is referenced once
+	uint64_t bad_wide = 0, children = 0;
+	std::vector<uint32_t> node_refs(n4.size(), 0), leaf_refs(leaves.size(), 0);
+	const int scale_word[3] = { 3, 10, 11 };
+	for (const Qbvh4NodeHost& q : n4) {
+		float origin[3]; memcpy(origin, q.w, 12);
+		for (int c = 0; c != 4; ++c) {
+			const int ref = (int) q.w[12 + c];
+			if (ref == 0x7FFFFFFF) continue;
+			++children;
+			if (ref >= 0) { if ((size_t) ref < n4.size()) node_refs[ref]++; else ++bad_wide; continue; }
+			auto it = std::lower_bound(leaves.begin(), leaves.end(), ref, [](const std::pair<int, LeafBox>& a, int r) { return a.first < r; });
+			if (it == leaves.end() || it->first != ref) { ++bad_wide; continue; }
+			leaf_refs[it - leaves.begin()]++;
+			for (int k = 0; k != 3; ++k) {
+				float scale; memcpy(&scale, &q.w[scale_word[k]], 4);
+				const double step = (double) scale / 32768.0;
+				const double lo = origin[k] + ((q.w[4 + k] >> (8 * c)) & 0xFFu) * step, hi = origin[k] + ((q.w[7 + k] >> (8 * c)) & 0xFFu) * step;
+				if (!(lo <= it->second.lo[k] && hi >= it->second.hi[k])) ++bad_wide;
+			}
+		}
+	}
+	for (size_t i = 1; i < n4.size(); ++i) bad_wide += node_refs[i] != 1;
+	for (uint32_t r : leaf_refs) bad_wide += r != 1;
+	report[0] = bad_order; report[1] = bad_binary; report[2] = bad_wide; report[3] = nodes.size(); report[4] = n4.size(); report[5] = ((uint64_t) depth << 32) | (uint64_t) (children * 100 / (n4.size() ? n4.size() : 1));
 	return 0;
 }
 

@@ -160,3 +160,25 @@ def test_hdr_writer(lib, tmp_path):
     px = raw[-4 * 24:][:4]
     e = px[3] - 136
     assert np.allclose([px[0] * 2.0 ** e, px[1] * 2.0 ** e, px[2] * 2.0 ** e], [0.5, 2.0, 0.125], rtol=0.02)
+
+
+@pytest.mark.parametrize("max_leaf", [1, 2, 4])
+def test_acceleration_structures_hold_their_invariants(max_leaf):
+    """Host-only: the binary BVH and its 4-wide collapse with 8-bit boxes (risltc_b200/csrc/bvh_build.cpp) for a generated
+    scene and for degenerate soups -- every triangle in exactly one leaf, every vertex inside its leaf box, every quantised
+    box containing the binary tree's box, every node referenced once. Hit / no-hit of the traversal kernels only depends on
+    the tree through these properties (the triangle test itself is the oracle's)."""
+    from risltc_b200 import api, scenes
+    scene = scenes.many_light_room(16, 60, seed=8, occluder_triangles=20000, width=64, height=36)
+    verts = scenes.dequantize_positions(scene["mesh"]).astype(np.float32).reshape(-1, 3, 3)
+    rng = np.random.default_rng(3)
+    soups = [verts,
+             verts[:1],                                                     # the whole scene is one leaf
+             np.repeat(verts[:1], 40, axis=0),                              # coincident triangles
+             (rng.normal(size=(3000, 1, 3)) * 50 + rng.normal(size=(3000, 3, 3)) * rng.uniform(1e-4, 5.0, (3000, 1, 1))).astype(np.float32),
+             np.concatenate([verts[:200], verts[:200] * np.float32(1e-3) + np.float32(900.0)])]   # tiny geometry far from the origin
+    for soup in soups:
+        r = api.check_bvh(soup, max_leaf)
+        assert r["bad_order"] == 0 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
+        assert r["wide_nodes"] <= r["binary_nodes"] and 1.0 <= r["children_per_node"] <= 4.0
+        assert 3 * r["depth"] + 1 <= 88      # the traversal stack of trace4_kernel (RL_T4_OVERFLOW)

@@ -8,13 +8,13 @@
 // atomicMin on the key {bits(t) : index}:
 //   * the hit conditions u >= 0, v >= 0, u + v <= 1 (times det > 0) are LINEAR functions of the pixel coordinates because
 //     the ray direction is (pixel_to_ray * (px, py, 1)); the three functions, evaluated with generous margins, reject
-//     64x64 tiles, 8x4 blocks and single pixels that the triangle cannot cover (homogeneous rasterisation: no near-plane
+//     32x32 tiles, 8x4 blocks and single pixels that the triangle cannot cover (homogeneous rasterisation: no near-plane
 //     clipping, no division);
 //   * a pixel that survives runs EXACTLY the decision sequence of bvh_closest_front (tri_terms / tri_exact / depth clip with
 //     the same roundings), so the buffer is bit-identical to the ray-cast one;
 //   * raster_setup_kernel (one thread per triangle) culls back faces and triangles in front of the near plane, rasterises
-//     triangles with a small screen bounding box itself and queues the others as units of 64x64 pixels;
-//     raster_tiles_kernel (persistent CTAs, one unit at a time through a ticket) classifies a unit's 128 blocks of 8x4
+//     triangles with a small screen bounding box itself and queues the others as units of 32x32 pixels;
+//     raster_tiles_kernel (persistent warps, one unit at a time through a ticket) classifies a unit's 32 blocks of 8x4
 //     pixels one per lane and tests the pixels of the surviving blocks one per lane;
 //   * raster_resolve_kernel turns the keys into the u32 ids (index | emitter << 31, 0xFFFFFFFF = background).
 #pragma once
@@ -23,7 +23,7 @@
 namespace RL_NS {
 
 #define RL_RASTER_SMALL 48u            // largest bounding box (pixels) that the setup thread rasterises itself
-#define RL_RASTER_TILE 64u             // a unit of raster_tiles_kernel is RL_RASTER_TILE^2 pixels
+#define RL_RASTER_TILE 32u             // a unit of raster_tiles_kernel is RL_RASTER_TILE^2 pixels = 32 blocks of 8x4, one per lane
 #define RL_RASTER_MAX_ITEMS (1u << 20) // queued triangles; scenes with more triangles than that use the BVH walk (api.cu)
 
 struct __align__(16) RasterItem {
@@ -203,50 +203,61 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 }
 
 __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUniforms f, Stripes st, RasterBuffers rb) {
-	__shared__ uint32_t sm_unit;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t lane = threadIdx.x & 31u;
 	const unsigned long long counter = *rb.counter;
 	const uint32_t item_count = min((uint32_t) (counter >> 32), RL_RASTER_MAX_ITEMS), unit_count = (uint32_t) counter;
+	if (item_count == 0u) return;
 	const RasterFrame rf = raster_frame(f);
-	while (true) {
-		__syncthreads();
-		if (threadIdx.x == 0) sm_unit = atomicAdd(rb.ticket, 1u);
-		__syncthreads();
-		const uint32_t unit = sm_unit;
-		if (unit >= unit_count) break;
-		// the item whose range of units contains `unit` (first_unit rises with the item index; dropped items leave a gap at the end)
-		uint32_t lo = 0, hi = item_count;
-		while (hi - lo > 1u) {
-			const uint32_t mid = (lo + hi) >> 1;
-			if (rb.items[mid].first_unit <= unit) lo = mid; else hi = mid;
-		}
-		if (item_count == 0u) continue;
-		const RasterItem it = rb.items[lo];
-		const uint32_t local = unit - it.first_unit;
-		if (local >= (uint32_t) it.ntx * it.nty) continue;   // a unit of a triangle that the setup thread kept for itself
-		// tiles are RL_RASTER_TILE pixels wide and RL_RASTER_TILE of this device's LOCAL rows high
-		const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_row = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
-		EdgeFunctions ef;
-		#pragma unroll
-		for (int i = 0; i != 3; ++i) { ef.fu[i] = it.fu[i]; ef.fv[i] = it.fv[i]; ef.fw[i] = it.fw[i]; ef.slack[i] = it.slack[i]; }
-		const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f;
-		const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + RL_RASTER_TILE, st.owned_rows) - 1u);
-		if (rect_rejected(ef, (float) tile_x, ty0, tx1, ty1)) continue;
-		const BvhTri tri = s.tris[it.tri];
-		const float K = early_z_constant(mk3(rf.o.x - tri.v0.x, rf.o.y - tri.v0.y, rf.o.z - tri.v0.z),
-			cross3(mk3(tri.e2.x, tri.e2.y, tri.e2.z), mk3(tri.e1.x, tri.e1.y, tri.e1.z)));
-		// 128 blocks of 8x4 pixels (8 across, 16 down), 32 per warp, classified one per lane
-		const uint32_t block = warp * 32u + lane;
-		const uint32_t bx = tile_x + (block & 7u) * 8u, brow = tile_row + (block >> 3) * 4u;
-		bool live = bx < f.width && brow < st.owned_rows;
-		if (live) live = !rect_rejected(ef, (float) bx, (float) st.global_row(brow), (float) min(bx + 7u, f.width - 1u), (float) st.global_row(min(brow + 3u, st.owned_rows - 1u)));
-		unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
-		while (todo) {
-			const uint32_t b = (uint32_t) __ffs(todo) - 1u;
-			todo &= todo - 1u;
-			const uint32_t blk = warp * 32u + b;
-			const uint32_t x = tile_x + (blk & 7u) * 8u + (lane & 7u), row = tile_row + (blk >> 3) * 4u + (lane >> 3);
-			if (x < f.width && row < st.owned_rows) raster_pixel(f, rf, tri, ef, K, x, st.global_row(row), row * f.width + x, rb.zbuf);
+	// Every WARP takes units on its own (no CTA barriers), `chunk` consecutive units per ticket: with few units (a 1080p frame
+	// of a small scene: ~4 per warp) one at a time keeps all warps busy to the end; with many (4K, 50 k triangles: > 100 per warp)
+	// consecutive units mostly belong to the same triangle, whose item search and loads are then done once per chunk. The next
+	// ticket is claimed before the current chunk is processed so that the atomic's round trip overlaps the pixel tests.
+	const uint32_t chunk = min(8u, max(1u, unit_count / (gridDim.x * 4u * 16u)));
+	uint32_t next_base = 0;
+	if (lane == 0) next_base = atomicAdd(rb.ticket, chunk);
+	next_base = __shfl_sync(0xFFFFFFFFu, next_base, 0);
+	RasterItem it;
+	it.first_unit = 0xFFFFFFFFu; it.ntx = it.nty = 0;
+	BvhTri tri;
+	EdgeFunctions ef;
+	float K = 0.0f;
+	while (next_base < unit_count) {
+		const uint32_t base = next_base, end = min(base + chunk, unit_count);
+		if (lane == 0) next_base = atomicAdd(rb.ticket, chunk);
+		next_base = __shfl_sync(0xFFFFFFFFu, next_base, 0);
+		for (uint32_t unit = base; unit != end; ++unit) {
+			if (unit - it.first_unit >= (uint32_t) it.ntx * it.nty) {
+				// the item whose range of units contains `unit` (first_unit rises with the item index; dropped items leave a gap at the end)
+				uint32_t lo = 0, hi = item_count;
+				while (hi - lo > 1u) {
+					const uint32_t mid = (lo + hi) >> 1;
+					if (__ldg(&rb.items[mid].first_unit) <= unit) lo = mid; else hi = mid;
+				}
+				it = rb.items[lo];
+				if (unit - it.first_unit >= (uint32_t) it.ntx * it.nty) continue;   // a unit of a triangle that the setup thread kept for itself
+				#pragma unroll
+				for (int i = 0; i != 3; ++i) { ef.fu[i] = it.fu[i]; ef.fv[i] = it.fv[i]; ef.fw[i] = it.fw[i]; ef.slack[i] = it.slack[i]; }
+				tri = s.tris[it.tri];
+				K = early_z_constant(mk3(rf.o.x - tri.v0.x, rf.o.y - tri.v0.y, rf.o.z - tri.v0.z),
+					cross3(mk3(tri.e2.x, tri.e2.y, tri.e2.z), mk3(tri.e1.x, tri.e1.y, tri.e1.z)));
+			}
+			const uint32_t local = unit - it.first_unit;
+			// tiles are RL_RASTER_TILE pixels wide and RL_RASTER_TILE of this device's LOCAL rows high
+			const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_row = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
+			const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f;
+			const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + RL_RASTER_TILE, st.owned_rows) - 1u);
+			if (rect_rejected(ef, (float) tile_x, ty0, tx1, ty1)) continue;
+			// 32 blocks of 8x4 pixels (4 across, 8 down), classified one per lane
+			const uint32_t bx = tile_x + (lane & 3u) * 8u, brow = tile_row + (lane >> 2) * 4u;
+			bool live = bx < f.width && brow < st.owned_rows;
+			if (live) live = !rect_rejected(ef, (float) bx, (float) st.global_row(brow), (float) min(bx + 7u, f.width - 1u), (float) st.global_row(min(brow + 3u, st.owned_rows - 1u)));
+			unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
+			while (todo) {
+				const uint32_t b = (uint32_t) __ffs(todo) - 1u;
+				todo &= todo - 1u;
+				const uint32_t x = tile_x + (b & 3u) * 8u + (lane & 7u), row = tile_row + (b >> 2) * 4u + (lane >> 3);
+				if (x < f.width && row < st.owned_rows) raster_pixel(f, rf, tri, ef, K, x, st.global_row(row), row * f.width + x, rb.zbuf);
+			}
 		}
 	}
 }

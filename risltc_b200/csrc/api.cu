@@ -64,8 +64,8 @@ struct risltc_device_s {
 	cudaEvent_t tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
-	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (512: 117 registers, 768: 80, 1024: 64 with spills)
-	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel (128, 256 or 512; 512 threads resident per SM)
+	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (768: 80 registers; 512: 117, slower)
+	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel (128, 256 or 384; measured best: 384)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
@@ -116,8 +116,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
-	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { int t = atoi(e); d->winner_resident = (t == 512 || t == 1024) ? (uint32_t) t : 768u; if (t != 768) d->winner_threads = 256; }
-	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 512 || t == 128 || t == 384 || t == 768) ? (uint32_t) t : 256u; }
+	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { d->winner_resident = (atoi(e) == 512) ? 512u : 768u; if (d->winner_resident == 512) d->winner_threads = 256; }
+	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 128 || t == 256) ? (uint32_t) t : 384u; }
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
 	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
@@ -462,17 +462,13 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		{
 			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles
-			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
+			const uint32_t threads = (d->winner_resident == 512) ? 256u : d->winner_threads, per_cta = threads / 32;
 			uint32_t wctas = (d->winner_resident / threads) * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (d->winner_resident == 768 && threads == 128) winner_kernel<128, 768><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (d->winner_resident == 768 && threads == 384) winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (d->winner_resident == 768 && threads == 768) winner_kernel<768, 768><<<wctas, 768, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (d->winner_resident == 768) winner_kernel<256, 768><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (d->winner_resident == 1024) winner_kernel<256, 1024><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 512) winner_kernel<512, 512><<<wctas, 512, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else winner_kernel<128, 512><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			if (d->winner_resident == 512) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 128) winner_kernel<128, 768><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256, 768><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		}
 		d->launches += 1;
 	}

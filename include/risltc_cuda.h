@@ -101,12 +101,15 @@ int risltc_cuda_set_frame_overlap(risltc_device_t* device, uint32_t mode);
 
 /* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
  * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index
- * (stripe_count = 1: the whole frame). Resets the accumulation buffer. */
+ * (stripe_count = 1: the whole frame). Resets the accumulation buffer (and detaches a buffer given
+ * to risltc_cuda_set_accum_buffer). */
 int risltc_cuda_resize(risltc_device_t* device, uint32_t width, uint32_t height,
 	uint32_t stripe_height, uint32_t stripe_index, uint32_t stripe_count);
 
 /* Let the accumulation target live in caller-owned device memory (e.g. a torch tensor that an
- * NCCL gather reads). `rows` is the number of rows this device owns; layout rows x width x RGBA32F. */
+ * NCCL gather reads); layout owned_rows x width x RGBA32F. NULL returns to the device's own buffer.
+ * risltc_cuda_resize recreates all render targets and therefore detaches a caller-owned buffer:
+ * attach again after every resize. */
 int risltc_cuda_set_accum_buffer(risltc_device_t* device, void* device_pointer);
 uint32_t risltc_cuda_owned_rows(const risltc_device_t* device);
 

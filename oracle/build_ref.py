@@ -37,6 +37,9 @@ VARIANTS = {
     "ris_ltc_weighted_v3": dict(light="reservoir", tech="ltc_cp", mis="weighted", S=1, L=1, vmin=3, vmax=3),
     "ris_ltc_optimal_v3": dict(light="reservoir", tech="ltc_cp", mis="optimal", S=1, L=1, vmin=3, vmax=3),
     "uni_psa_biased_fast_v5": dict(light="uniform", tech="psa_biased", mis="power", S=1, L=1, fast_atan=1, vmin=3, vmax=5),
+    # the largest polygons the reference supports (MAX_POLYGONAL_LIGHT_VERTEX_COUNT up to 7, main.c:191-204)
+    "ris_psa_v6": dict(light="reservoir", tech="psa", mis="optimal_clamped", S=1, L=1, vmin=6, vmax=6),
+    "uni_psa_v7": dict(light="uniform", tech="psa", mis="optimal_clamped", S=1, L=1, vmin=3, vmax=7),
     # control: the default variant compiled the way a GLSL compiler may compile it (a*b+c contracted to fma). Its
     # distance to ris_ltc_v3 is the reference's own sensitivity to legal rounding changes (tests/test_gpu_frames.py).
     "ris_ltc_v3_fma": dict(light="reservoir", tech="ltc_cp", mis="optimal_clamped", S=1, L=1, vmin=3, vmax=3, contract=True),

@@ -133,13 +133,15 @@ inline float max(float a, float b) { return std::fmax(a, b); }
 inline float min(float a, float b) { return std::fmin(a, b); }
 inline float clamp(float x, float lo, float hi) { return std::fmin(std::fmax(x, lo), hi); }
 inline float fma(float a, float b, float c) { return std::fmaf(a, b, c); }
-inline float sin(float x) { return std::sin(x); }
-inline float cos(float x) { return std::cos(x); }
-inline float atan(float x) { return std::atan(x); }
-inline float atan(float y, float x) { return std::atan2(y, x); }
-inline float acos(float x) { return std::acos(x); }
-inline float asin(float x) { return std::asin(x); }
-inline float tan(float x) { return std::tan(x); }
+// transcendental functions: GLSL prescribes no rounding, the oracle defines them as the correctly rounded fp32 value
+// (double-precision libm rounded once; see glsl_atan in risltc_oracle.c)
+inline float sin(float x) { return (float) std::sin((double) x); }
+inline float cos(float x) { return (float) std::cos((double) x); }
+inline float atan(float x) { return (float) std::atan((double) x); }
+inline float atan(float y, float x) { return (float) std::atan2((double) y, (double) x); }
+inline float acos(float x) { return (float) std::acos((double) x); }
+inline float asin(float x) { return (float) std::asin((double) x); }
+inline float tan(float x) { return (float) std::tan((double) x); }
 inline float pow(float a, float b) { return std::pow(a, b); }
 inline float log2(float x) { return std::log2(x); }
 inline float exp2(float x) { return std::exp2(x); }

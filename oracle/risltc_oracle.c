@@ -110,6 +110,17 @@ float orc_noise_next(uint32_t* seed) {
 
 /* --------------------------------------------------------- polygon helpers */
 
+/* GLSL prescribes no rounding for atan / acos / sin / cos (every driver has its own), so the oracle has to DEFINE them:
+ * the correctly rounded fp32 value, obtained as the double-precision libm function rounded once (the double result is
+ * within an ulp of the true value; the chance that rounding it to fp32 differs from rounding the true value is ~2^-29 per
+ * call). The definition is independent of the libm version and can be met bit for bit by the CUDA kernels' exact mode
+ * (csrc/common.cuh, RL_CR_LIBM). oracle/glsl_shim.hpp gives the compiled reference GLSL the same definition. The host
+ * arithmetic below (light rotation, camera matrices) keeps cosf / sinf / tanf: it is C in the reference too. */
+static inline float glsl_atan(float x) { return (float) atan((double) x); }
+static inline float glsl_acos(float x) { return (float) acos((double) x); }
+static inline float glsl_sin(float x) { return (float) sin((double) x); }
+static inline float glsl_cos(float x) { return (float) cos((double) x); }
+
 /* polygon_sampling.glsl:84-98 */
 static float fast_positive_atan(float y) {
 	float rx, ry, rz;
@@ -129,7 +140,7 @@ static float fast_positive_atan(float y) {
 static float positive_atan(float tangent, int fast_atan) {
 	if (fast_atan) return fast_positive_atan(tangent);
 	float offset = (tangent < 0.0f) ? ORC_PI : 0.0f;
-	return atanf(tangent) + offset;
+	return glsl_atan(tangent) + offset;
 }
 
 /* polygon_sampling.glsl:184-186 */
@@ -472,7 +483,7 @@ void orc_sample_psa(float out_dir[3], const orc_psa_polygon_t* polygon, float u0
 		float sqrt_det = sqrtf(get_ellipse_det(outer_ellipse));
 		float angle = 2.0f * target * sqrt_det;
 		v2 t = rotate_90(ellipse_transform(outer_ellipse, dir_0));
-		float ca = cosf(angle) * sqrt_det, sa = sinf(angle);
+		float ca = glsl_cos(angle) * sqrt_det, sa = glsl_sin(angle);
 		sampled = mk2(ca * dir_0.x + sa * t.x, ca * dir_0.y + sa * t.y);
 		float s = sqrtf(u1 / get_ellipse_direction_factor_rsq(outer_ellipse, sampled));
 		sampled = mul2(sampled, s);
@@ -573,7 +584,7 @@ void orc_get_ltc_coefficients(orc_ltc_t* ltc, const orc_scene_t* scene, float fr
 {
 	v3 normal = ld3(normal_), outgoing = ld3(outgoing_), pos = ld3(position);
 	float normal_dot_outgoing = dot3(normal, outgoing);
-	float inclination = acosf(clampf(normal_dot_outgoing, 0.0f, 1.0f));
+	float inclination = glsl_acos(clampf(normal_dot_outgoing, 0.0f, 1.0f));
 	float tu = fmaf(sqrtf(clampf(roughness, 0.0f, 1.0f)), c[2], c[3]);
 	float tv = fmaf(inclination, c[4], c[5]);
 	float tl = fmaf(clampf(fresnel_0, 0.0f, 1.0f), c[0], c[1]);

@@ -1,11 +1,10 @@
 // api.cu -- C ABI of librisltc_cuda.so (include/risltc_cuda.h) and kernel launches.
-#include "../../include/risltc_cuda.h"
+#include "internal.h"
 #include "kernels.cuh"
 #include "shade_fast.cuh"
 #include "trace4.cuh"
 #include "raster.cuh"
 #include "bvh_build.h"
-#include "clip_rotation_table.inc"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,12 +17,12 @@ using namespace exact;
 
 static thread_local std::string g_last_error;
 
-static int fail(const char* what, const char* detail) {
+int rl_fail(const char* what, const char* detail) {
 	g_last_error = std::string(what) + (detail ? std::string(": ") + detail : std::string());
 	printf("risltc_cuda: %s\n", g_last_error.c_str());
 	return 1;
 }
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, cudaGetErrorString(e_)); } while (0)
+#define fail rl_fail
 
 struct risltc_device_s {
 	int ordinal = 0;
@@ -65,6 +64,7 @@ struct risltc_device_s {
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
 	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (768: 80 registers; 512: 117, slower)
+	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel (128, 256 or 384; measured best: 384)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
@@ -75,11 +75,14 @@ struct risltc_device_s {
 	uint32_t timed_frames = 0;
 };
 
-static int use(risltc_device_t* d) {
+int rl_use(risltc_device_t* d) {
 	if (!d) return fail("null device", nullptr);
 	CU(cudaSetDevice(d->ordinal));
 	return 0;
 }
+#define use rl_use
+const SceneView& rl_view(const risltc_device_t* d) { return d->view; }
+int rl_sm_count(const risltc_device_t* d) { return d->sm_count; }
 
 extern "C" const char* risltc_cuda_last_error(void) { return g_last_error.c_str(); }
 
@@ -101,7 +104,6 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaEventCreateWithFlags(&d->ev_resolved[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_resolved[1], cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
-	CU(cudaMemcpyToSymbol(c_clip_rotation, h_clip_rotation, sizeof(h_clip_rotation)));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	d->sm_count = prop.multiProcessorCount;
@@ -118,6 +120,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
 	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { d->winner_resident = (atoi(e) == 512) ? 512u : 768u; if (d->winner_resident == 512) d->winner_threads = 256; }
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 128 || t == 256) ? (uint32_t) t : 384u; }
+	if (const char* e = getenv("RISLTC_WINNER")) d->winner_cr = strcmp(e, "cr") == 0;
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
 	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
@@ -190,6 +193,8 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	uint32_t max_leaf = 2;   // measured best for the 4-wide any-hit kernel (a triangle test costs about as much as three box tests)
 	if (const char* e = getenv("RISLTC_BVH_LEAF")) max_leaf = (uint32_t) atoi(e);
 	build_bvh(verts.data(), T, nodes, order, max_leaf);
+	// gbuffer_kernel, the exact-precision paths and trace_kernel walk the binary tree with RL_STACK entries per thread
+	if (bvh_depth(nodes) > RL_STACK) return fail("upload_scene: the binary acceleration structure is deeper than the traversal stack", nullptr);
 	std::vector<BvhNode> dn(nodes.size());
 	for (size_t i = 0; i != nodes.size(); ++i) {
 		const BvhNodeHost& n = nodes[i];
@@ -352,7 +357,8 @@ extern "C" int risltc_cuda_set_variant(risltc_device_t* d, const risltc_variant_
 	if (!v) return fail("set_variant: null variant", nullptr);
 	if (v->polygon_technique > TECH_LTC_CP || v->mis_heuristic > MIS_OPTIMAL || v->light_sampling > 1) return fail("set_variant: enum out of range", nullptr);
 	if (v->sample_count == 0 || v->light_samples == 0) return fail("set_variant: sample counts must be positive", nullptr);
-	if (v->max_light_vertices < 3 || v->max_light_vertices > 4) return fail("set_variant: kernels are instantiated for 3 and 4 vertex lights", nullptr);
+	if (v->max_light_vertices < 3 || v->max_light_vertices > 7 || v->min_light_vertices < 3 || v->min_light_vertices > v->max_light_vertices)
+		return fail("set_variant: lights have 3 to 7 vertices (main.c:191-204) and min_light_vertices <= max_light_vertices", nullptr);
 	CU(cudaStreamSynchronize(d->stream));
 	memcpy(&d->variant, v, sizeof(Variant));
 	return allocate_ray_buffers(d);
@@ -381,8 +387,8 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	if (use(d)) return 1;
 	if (width == 0 || height == 0 || stripe_count == 0 || stripe_index >= stripe_count || stripe_height == 0) return fail("resize: bad extent or stripe layout", nullptr);
 	CU(cudaStreamSynchronize(d->stream));
-	void* external = (d->px.accum && d->px.accum != d->own_accum) ? (void*) d->px.accum : nullptr;
-	(void) external;
+	// the render targets are recreated: accumulation restarts in the device's own buffer (a caller-owned buffer attached
+	// with set_accum_buffer belongs to the old extent and has to be attached again, include/risltc_cuda.h)
 	free_targets(d);
 	uint32_t owned = 0;
 	for (uint32_t y0 = stripe_index * stripe_height; y0 < height; y0 += stripe_height * stripe_count)
@@ -465,21 +471,15 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 			const uint32_t threads = (d->winner_resident == 512) ? 256u : d->winner_threads, per_cta = threads / 32;
 			uint32_t wctas = (d->winner_resident / threads) * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (d->winner_resident == 512) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			if (d->winner_cr) { if (rl_launch_winner_cr(d->view, f, d->stripes, px, tiles_x, tile_count, std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), stream)) return 1; }
+			else if (d->winner_resident == 512) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else if (threads == 128) winner_kernel<128, 768><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else if (threads == 256) winner_kernel<256, 768><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		}
 		d->launches += 1;
 	}
-	else if (v.max_light_vertices == 3) {
-		if (defer) shade_kernel<3, true><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
-		else shade_kernel<3, false><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
-	}
-	else {
-		if (defer) shade_kernel<4, true><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
-		else shade_kernel<4, false><<<grid, 128, 0, stream>>>(d->view, f, v, d->stripes, px);
-	}
+	else return rl_launch_generic_shade(d->view, f, v, d->stripes, px, grid, defer, stream);
 	return 0;
 }
 
@@ -492,6 +492,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
 	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
 	CU(cudaMemsetAsync(d->px.ticket, 0, 4 * sizeof(unsigned int), d->stream));
+	if (d->set2_ready) CU(cudaMemsetAsync(d->px2.ticket, 0, 4 * sizeof(unsigned int), d->stream));   // a failed call must not leave tickets behind
 	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
 	d->timed_frames = frame_count;
 	CU(cudaEventRecord(d->ev[0], d->stream));
@@ -689,4 +690,51 @@ extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t
 
 extern "C" void* risltc_cuda_stream(risltc_device_t* d) { return d ? (void*) d->stream : nullptr; }
 
-#include "kat.cuh"
+// ---- known-answer entry point of the shadow-ray kernels (the other risltc_cuda_kat_* live in kat.cu)
+template <typename T>
+struct DeviceArray {
+	T* p = nullptr; size_t n = 0;
+	int init(const T* host, size_t count) {
+		n = count;
+		if (cudaMalloc(&p, sizeof(T) * (count ? count : 1)) != cudaSuccess) return 1;
+		if (host && cudaMemcpy(p, host, sizeof(T) * count, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+		return 0;
+	}
+	int fetch(T* host) { return cudaMemcpy(host, p, sizeof(T) * n, cudaMemcpyDeviceToHost) != cudaSuccess; }
+	~DeviceArray() { cudaFree(p); }
+};
+#define KAT_GRID(count) ((count) + 127) / 128, 128
+
+// The production shadow-ray kernels (kind 4: trace4_kernel, 2: trace_kernel) on an array of rays with t_min = 1e-3:
+// the rays are laid out as one ray slot of `count` pixels, exactly what the shading kernels leave behind.
+__global__ void kat_trace_fill_kernel(const float* rays, float4* origin, float4* ray_a, float4* ray_b, uint32_t count) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const float* r = rays + 8 * (size_t) i;
+	origin[i] = make_float4(r[0], r[1], r[2], 0.0f);
+	ray_a[i] = make_float4(r[4], r[5], r[6], r[7]);
+	ray_b[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+}
+__global__ void kat_trace_read_kernel(const float4* ray_b, uint32_t* hits, uint32_t count) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) hits[i] = (ray_b[i].w == 2.0f) ? 1u : 0u;
+}
+extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind) {
+	if (use(d)) return 1;
+	if (!d->nodes || !d->nodes4) return fail("kat_trace: upload_scene first", nullptr);
+	if (kind != 2 && kind != 4) return fail("kat_trace: kind must be 2 or 4", nullptr);
+	DeviceArray<float> r; DeviceArray<uint32_t> h; DeviceArray<float4> og, ra, rb; DeviceArray<unsigned int> ticket;
+	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 4))
+		return fail("kat_trace: allocation failed", nullptr);
+	CU(cudaMemset(ticket.p, 0, 4 * sizeof(unsigned int)));
+	PixelBuffers px = {};
+	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
+	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
+	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
+	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
+	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
+	CU(cudaDeviceSynchronize());
+	if (h.fetch(hits)) return fail("kat_trace: read-back failed", nullptr);
+	return 0;
+}
+

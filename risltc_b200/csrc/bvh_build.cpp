@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <utility>
 
 namespace {
 
@@ -145,6 +146,20 @@ void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeH
 		nodes.push_back(n);
 	}
 	order.swap(b.order);
+}
+
+uint32_t bvh_depth(const std::vector<BvhNodeHost>& nodes) {
+	if (nodes.empty()) return 0;
+	uint32_t deepest = 0;
+	std::vector<std::pair<int, uint32_t>> todo(1, std::make_pair(0, 1u));
+	while (!todo.empty()) {
+		const std::pair<int, uint32_t> it = todo.back(); todo.pop_back();
+		deepest = std::max(deepest, it.second);
+		const BvhNodeHost& n = nodes[it.first];
+		if (n.left >= 0) todo.push_back(std::make_pair(n.left, it.second + 1u));
+		if (n.right >= 0) todo.push_back(std::make_pair(n.right, it.second + 1u));
+	}
+	return deepest;
 }
 
 // ---- four children per node, 8-bit boxes

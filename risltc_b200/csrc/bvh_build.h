@@ -15,6 +15,9 @@ void dequantize_mesh_for_bvh(const uint32_t* quantized_positions, uint64_t trian
 // verts: 9 floats per triangle. order[slot] = triangle index stored at that leaf slot.
 void build_bvh(const float* verts, uint64_t triangle_count, std::vector<BvhNodeHost>& nodes, std::vector<uint32_t>& order, uint32_t max_leaf = 4);
 
+// Levels of inner nodes of the binary tree (the per-thread traversal stacks hold one entry per level at most).
+uint32_t bvh_depth(const std::vector<BvhNodeHost>& nodes);
+
 // The binary tree collapsed to four children per node with 8-bit boxes (layout: Qbvh4Node in common.cuh, 16 words).
 // Every quantised box contains the binary tree's (padded) box of the same child.
 struct Qbvh4NodeHost { uint32_t w[16]; };

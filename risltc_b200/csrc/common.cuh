@@ -143,6 +143,22 @@ __device__ __forceinline__ float unorm16(uint32_t q) {
 __device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// GLSL's atan / acos / sin / cos have no prescribed rounding; the oracle (oracle/risltc_oracle.c, oracle/glsl_shim.hpp)
+// defines them as the CORRECTLY ROUNDED fp32 value, computed as the double-precision function rounded once. A translation
+// unit compiled with RL_CR_LIBM (generic.cu, kat.cu, winner_cr.cu) does the same -- its transcendental results are then
+// bit-identical to the oracle's (up to the ~2^-29 chance per call that the double result straddles a rounding boundary) --
+// and one without it (the production kernels of api.cu) uses CUDA's fp32 functions (1-2 ulp).
+#ifdef RL_CR_LIBM
+__device__ __forceinline__ float rl_atan(float x) { return (float) atan((double) x); }
+__device__ __forceinline__ float rl_acos(float x) { return (float) acos((double) x); }
+__device__ __forceinline__ float rl_sin(float x) { return (float) sin((double) x); }
+__device__ __forceinline__ float rl_cos(float x) { return (float) cos((double) x); }
+#else
+__device__ __forceinline__ float rl_atan(float x) { return atanf(x); }
+__device__ __forceinline__ float rl_acos(float x) { return acosf(x); }
+__device__ __forceinline__ float rl_sin(float x) { return sinf(x); }
+__device__ __forceinline__ float rl_cos(float x) { return cosf(x); }
+#endif
 __device__ __forceinline__ float3 normalize3(float3 a) { return scale3(a, inversesqrt(dot3(a, a))); }
 __device__ __forceinline__ float2 normalize2(float2 a) { return scale2(a, inversesqrt(dot2(a, a))); }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }

@@ -1,7 +1,17 @@
-// kat.cuh -- known-answer entry points: the device functions of the shading kernel run on
-// arrays, one thread per item, so that tests can compare them with the oracle function by function.
-// Included at the end of api.cu.
-#pragma once
+// kat.cu -- known-answer entry points: the device functions of the shading kernels run on arrays, one thread per item,
+// so that tests can compare them with the oracle function by function (include/risltc_cuda.h, risltc_cuda_kat_*).
+// risltc_cuda_kat_trace, which runs the production shadow-ray kernels, lives in api.cu next to them.
+// a namespace of its own: the host-side stubs of the shared __device__ functions must not collide with api.cu's
+#define RL_NS kat
+#define RL_CR_LIBM 1   // transcendental functions correctly rounded, like the oracle (common.cuh)
+#include "internal.h"
+#include "shading.cuh"
+#include "bvh.cuh"
+#include <cstdio>
+
+using namespace RL_NS;
+#define use rl_use
+#define fail rl_fail
 
 template <int V>
 __global__ void kat_clip_kernel(float* polygons, uint32_t* counts, uint32_t count, uint32_t min_vertices) {
@@ -153,10 +163,10 @@ extern "C" int risltc_cuda_kat_noise(risltc_device_t* d, uint32_t width, uint32_
 
 extern "C" int risltc_cuda_kat_ltc_coefficients(risltc_device_t* d, const float* inputs, const float c[6], float* out, uint32_t count) {
 	if (use(d)) return 1;
-	if (!d->ltc_rgba) return fail("kat_ltc_coefficients: upload_ltc first", nullptr);
+	if (!rl_view(d).ltc_rgba) return fail("kat_ltc_coefficients: upload_ltc first", nullptr);
 	DeviceArray<float> in, o;
 	if (in.init(inputs, (size_t) count * 11) || o.init(nullptr, (size_t) count * 33)) return fail("kat_ltc_coefficients: allocation failed", nullptr);
-	kat_ltc_kernel<<<KAT_GRID(count)>>>(d->view, in.p, c[0], c[1], c[2], c[3], c[4], c[5], o.p, count);
+	kat_ltc_kernel<<<KAT_GRID(count)>>>(rl_view(d), in.p, c[0], c[1], c[2], c[3], c[4], c[5], o.p, count);
 	CU(cudaDeviceSynchronize());
 	if (o.fetch(out)) return fail("kat_ltc_coefficients: read-back failed", nullptr);
 	return 0;
@@ -164,45 +174,12 @@ extern "C" int risltc_cuda_kat_ltc_coefficients(risltc_device_t* d, const float*
 
 extern "C" int risltc_cuda_kat_any_hit(risltc_device_t* d, const float* rays, uint32_t* hits, uint32_t count) {
 	if (use(d)) return 1;
-	if (!d->nodes) return fail("kat_any_hit: upload_scene first", nullptr);
+	if (!rl_view(d).nodes) return fail("kat_any_hit: upload_scene first", nullptr);
 	DeviceArray<float> r; DeviceArray<uint32_t> h;
 	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count)) return fail("kat_any_hit: allocation failed", nullptr);
-	kat_any_hit_kernel<<<KAT_GRID(count)>>>(d->view, r.p, h.p, count);
+	kat_any_hit_kernel<<<KAT_GRID(count)>>>(rl_view(d), r.p, h.p, count);
 	CU(cudaDeviceSynchronize());
 	if (h.fetch(hits)) return fail("kat_any_hit: read-back failed", nullptr);
-	return 0;
-}
-
-// The production shadow-ray kernels (kind 4: trace4_kernel, 2: trace_kernel) on an array of rays with t_min = 1e-3:
-// the rays are laid out as one ray slot of `count` pixels, exactly what the shading kernels leave behind.
-__global__ void kat_trace_fill_kernel(const float* rays, float4* origin, float4* ray_a, float4* ray_b, uint32_t count) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
-	const float* r = rays + 8 * (size_t) i;
-	origin[i] = make_float4(r[0], r[1], r[2], 0.0f);
-	ray_a[i] = make_float4(r[4], r[5], r[6], r[7]);
-	ray_b[i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-}
-__global__ void kat_trace_read_kernel(const float4* ray_b, uint32_t* hits, uint32_t count) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < count) hits[i] = (ray_b[i].w == 2.0f) ? 1u : 0u;
-}
-extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind) {
-	if (use(d)) return 1;
-	if (!d->nodes || !d->nodes4) return fail("kat_trace: upload_scene first", nullptr);
-	if (kind != 2 && kind != 4) return fail("kat_trace: kind must be 2 or 4", nullptr);
-	DeviceArray<float> r; DeviceArray<uint32_t> h; DeviceArray<float4> og, ra, rb; DeviceArray<unsigned int> ticket;
-	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 4))
-		return fail("kat_trace: allocation failed", nullptr);
-	CU(cudaMemset(ticket.p, 0, 4 * sizeof(unsigned int)));
-	PixelBuffers px = {};
-	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
-	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
-	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
-	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
-	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
-	CU(cudaDeviceSynchronize());
-	if (h.fetch(hits)) return fail("kat_trace: read-back failed", nullptr);
 	return 0;
 }
 
@@ -229,7 +206,7 @@ extern "C" int risltc_cuda_kat_exact_math(risltc_device_t* d, uint64_t mismatche
 	DeviceArray<unsigned long long> o;
 	if (o.init(nullptr, 16)) return fail("kat_exact_math: allocation failed", nullptr);
 	CU(cudaMemset(o.p, 0, 16 * sizeof(unsigned long long)));
-	kat_exact_math_kernel<<<d->sm_count * 8, 256>>>(o.p);
+	kat_exact_math_kernel<<<rl_sm_count(d) * 8, 256>>>(o.p);
 	CU(cudaDeviceSynchronize());
 	unsigned long long h[16];
 	if (o.fetch(h)) return fail("kat_exact_math: read-back failed", nullptr);

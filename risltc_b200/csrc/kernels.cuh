@@ -237,6 +237,13 @@ __global__ void __launch_bounds__(128) shade_kernel(SceneView s, FrameUniforms f
 #define RL_TRACE_REFILL 6      // hand out staged rays when this many lanes are idle
 #define RL_LEAF_STACK 24
 
+// Reciprocal of a direction component for the fma slab tests t = plane * inv - o * inv. A zero (or flushed) component would
+// give inv = inf and then inf - inf = NaN on BOTH planes of the axis, which fminf / fmaxf drop: the axis would count as
+// overlapping even when the origin lies outside the slab -- and for o * inv = NaN with a finite other plane a box could be
+// missed. Clamping |d| to 1e-30 keeps every product finite (planes and origins are < 1e6) and the test exact enough for
+// padded boxes: t = +-1e30 * (plane - o) has the sign the true limit has.
+__device__ __forceinline__ float box_reciprocal(float d) { return approx_rcp(fabsf(d) < 1.0e-30f ? copysignf(1.0e-30f, d) : d); }
+
 __device__ __forceinline__ bool slab_fma(float4 lo_hi_a, float2 hi_b, float3 inv, float3 oi, float t_min, float t_max) {
 	// box {lo.xyz, hi.x} + {hi.y, hi.z}; t = plane * inv - o * inv (boxes are padded, see bvh.cuh)
 	float ax = fmaf(lo_hi_a.x, inv.x, -oi.x), bx = fmaf(lo_hi_a.w, inv.x, -oi.x);
@@ -304,9 +311,8 @@ __global__ void __launch_bounds__(128) trace_kernel(SceneView s, PixelBuffers px
 					const float4 a0 = stage[mine][0], a1 = stage[mine][1];
 					ray = __float_as_uint(a1.w); busy = true;
 					o = mk3(a0.x, a0.y, a0.z); d = mk3(a1.x, a1.y, a1.z); t_max = a0.w;
-					// box tests only: an approximate reciprocal is covered by the padding of the boxes; a zero component
-					// gives inf and then inf / nan slab bounds that fminf / fmaxf ignore like the exact form does
-					inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
+					// box tests only: an approximate reciprocal is covered by the padding of the boxes (box_reciprocal keeps it finite)
+					inv = mk3(box_reciprocal(d.x), box_reciprocal(d.y), box_reciprocal(d.z));
 					oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
 					node = 0; nsp = 0; lsp = 0; tri_i = tri_end = 0u;
 				}

@@ -12,8 +12,11 @@
 
 namespace RL_NS {
 
-// rot[n - 3][above_mask]: slot order of the clipped polygon (tools/gen_clip_table.py)
-__constant__ unsigned char c_clip_rotation[5][128];
+// rot[n - 3][above_mask]: slot order of the clipped polygon (tools/gen_clip_table.py); statically initialised, so every
+// translation unit that includes this header carries its own copy and nothing is uploaded at run time
+__constant__ unsigned char c_clip_rotation[5][128] =
+#include "clip_rotation_table.inc"
+;
 
 // ------------------------------------------------------------------ noise
 // noise_utility.glsl:26-95. The image is defined by the ORDER of these draws.
@@ -156,7 +159,7 @@ __device__ void ltc_fetch(const SceneView& s, float u, float v, float layer_coor
 __device__ LtcFrame make_ltc_frame(const SceneView& s, float fresnel_0, float roughness, float3 pos, float3 normal, float3 outgoing, const float* c) {
 	LtcFrame l;
 	float n_dot_o = dot3(normal, outgoing);
-	float inclination = acosf(clampf(n_dot_o, 0.0f, 1.0f));
+	float inclination = rl_acos(clampf(n_dot_o, 0.0f, 1.0f));
 	float d[6];
 	ltc_fetch(s, fmaf(sqrtf(clampf(roughness, 0.0f, 1.0f)), c[2], c[3]), fmaf(inclination, c[4], c[5]), fmaf(clampf(fresnel_0, 0.0f, 1.0f), c[0], c[1]), d);
 	// mat3(d0.x,0,-d0.y, 0,d0.z,0, d0.w,0,d1.x) is column-major: S[0][0]=d0.x, S[2][0]=-d0.y, S[1][1]=d0.z, S[0][2]=d0.w, S[2][2]=d1.x
@@ -287,7 +290,7 @@ __device__ __forceinline__ float fast_positive_atan(float y) {   // :84-98
 }
 __device__ __forceinline__ float positive_atan(float tangent, bool fast) {   // :105-112
 	if (fast) return fast_positive_atan(tangent);
-	return atanf(tangent) + ((tangent < 0.0f) ? RL_PI : 0.0f);
+	return rl_atan(tangent) + ((tangent < 0.0f) ? RL_PI : 0.0f);
 }
 __device__ __forceinline__ float area_from_tangents(float inner_rsqrt, float inner_tan, float outer_rsqrt, float outer_tan, bool fast) {   // :381-386
 	float inner_area = inner_rsqrt * positive_atan(inner_tan, fast);
@@ -453,7 +456,7 @@ __device__ __noinline__ float3 psa_sample(const PsaPolygon<P>& p, float u0, floa
 		float sqrt_det = sqrtf(ellipse_det(outer));
 		float angle = 2.0f * target * sqrt_det;
 		float2 t = rotate_90(ellipse_transform(outer, d0));
-		float ca = cosf(angle) * sqrt_det, sa = sinf(angle);
+		float ca = rl_cos(angle) * sqrt_det, sa = rl_sin(angle);
 		s = mk2(ca * d0.x + sa * t.x, ca * d0.y + sa * t.y);
 		s = scale2(s, sqrtf(u1 / ellipse_dir_factor_rsq(outer, s)));
 	}

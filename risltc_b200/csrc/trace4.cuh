@@ -1,7 +1,7 @@
 // trace4.cuh -- kernel (3), shadow rays (get_polygon_visibility, shading_pass.frag.glsl:112-129), second generation.
 //
 // Why it replaces trace_kernel (kernels.cuh) as the default: ncu showed the binary-tree kernel bound by the L1 data
-// pipe (l1tex__data_pipe_lsu_wavefronts 90 % of peak, profiles/r1_ncu_trace_kernel_l1.txt): every lane fetched 64 bytes
+// pipe (l1tex__data_pipe_lsu_wavefronts 90 % of peak, profiles/r1_ncu_trace_kernel.txt): every lane fetched 64 bytes
 // per TWO child boxes with four 16-byte loads, each of which costs a tag lookup per distinct node in the warp, and kept
 // its stacks in local memory, where lanes with different stack heights hit different lines. Here
 //   * a node holds FOUR children in the same 64 bytes (Qbvh4Node: boxes quantised to 8 bits relative to the node), so a
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 					ray = __float_as_uint(a1.w); busy = true;
 					o = mk3(a0.x, a0.y, a0.z); d = mk3(a1.x, a1.y, a1.z); t_max = a0.w;
 					// box tests only: the error of the approximate reciprocal is covered by the outward rounding of the boxes
-					inv = mk3(approx_rcp(d.x), approx_rcp(d.y), approx_rcp(d.z));
+					inv = mk3(box_reciprocal(d.x), box_reciprocal(d.y), box_reciprocal(d.z));
 					oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
 					node = 0; nsp = 0; lsp = 0; spilled = 0; tri_i = tri_end = 0u;
 				}

@@ -3,7 +3,7 @@
  * 4x4 inverse and Wang hash (math_utilities.h:24-57), noise words (noise_table.c:24-28).
  * Everything is fp32 with the reference's operation order, so that the 256-byte constant
  * block and the light records come out bit-identical (checked against the reference's own
- * polygonal_light.c / camera.c / math_utilities.h compiled as-is, tests/test_ref_host.py). */
+ * polygonal_light.c / camera.c / math_utilities.h compiled as-is, tests/test_host_layer.py). */
 #include "risltc_host.h"
 #include <math.h>
 #include <stdlib.h>
@@ -22,7 +22,6 @@ static char* duplicate_string(const char* s) {
 int set_polygonal_light_vertex_count(polygonal_light_t* light, uint32_t vertex_count) {
 	if (vertex_count == light->vertex_count && light->vertices_plane_space && light->vertices_world_space)
 		return 0;
-	size_t bytes = sizeof(float) * 4 * vertex_count;
 	float* plane_space = (float*) calloc(vertex_count ? vertex_count : 1, sizeof(float) * 4);
 	if (light->vertices_plane_space) {
 		uint32_t keep = (vertex_count < light->vertex_count) ? vertex_count : light->vertex_count;
@@ -32,7 +31,6 @@ int set_polygonal_light_vertex_count(polygonal_light_t* light, uint32_t vertex_c
 	free(light->vertices_world_space);
 	light->vertices_plane_space = plane_space;
 	light->vertices_world_space = (float*) calloc(vertex_count ? vertex_count : 1, sizeof(float) * 4);
-	(void) bytes;
 	/* The reference compares after assigning, so it always reports "unchanged" (polygonal_light.c:39-40) */
 	light->vertex_count = vertex_count;
 	return 0;
@@ -70,7 +68,7 @@ void update_polygonal_light(polygonal_light_t* light) {
 	/* signed area of the triangle fan around vertex 0 */
 	float signed_area = 0.0f;
 	const float* p0 = light->vertices_plane_space;
-	for (uint32_t i = 0; i + 2 < light->vertex_count + 0u && i != light->vertex_count - 2; ++i) {
+	for (uint32_t i = 0; i + 2 < light->vertex_count; ++i) {
 		const float* pa = light->vertices_plane_space + 4 * (i + 2);
 		const float* pb = light->vertices_plane_space + 4 * (i + 1);
 		float ax = pa[0] - p0[0], bx = pb[0] - p0[0];

@@ -189,7 +189,8 @@ def _random_rotation(rng):
 def many_light_room(light_count=64, box_count=200, seed=2, occluder_triangles=0, width=1920, height=1080, vertex_count=3):
     """Configs C2/C3/C5 (and C4 with occluder_triangles > 0): a 20x20x6 m room with random boxes,
     `light_count` polygonal lights on the ceiling and walls (side 0.2-1 m, radiance log-uniform in
-    [1, 50] per channel) and, optionally, a field of small random triangles between floor and lights."""
+    [1, 50] per channel) and, optionally, a field of small random triangles between floor and lights.
+    vertex_count: vertices per light, or (min, max) for lights that cycle through every count of the range."""
     rng = np.random.default_rng(seed)
     materials = default_materials(8) + [dict(name="emitter", base_color=[1.0, 1.0, 1.0], roughness=1.0, metalicity=0.0)]
     emitter = len(materials) - 1
@@ -216,8 +217,9 @@ def many_light_room(light_count=64, box_count=200, seed=2, occluder_triangles=0,
         normal = normal + rng.normal(scale=0.15, size=3)
         side = rng.uniform(0.2, 1.0)
         phase = rng.uniform(0, 2 * np.pi)
-        ang = phase + np.arange(vertex_count) * (2 * np.pi / vertex_count)
-        verts = np.stack([np.cos(ang), np.sin(ang)], axis=1) * (0.5 + 0.3 * rng.random((vertex_count, 1)))
+        vc = vertex_count if np.isscalar(vertex_count) else int(vertex_count[0] + len(lights) % (vertex_count[1] - vertex_count[0] + 1))
+        ang = phase + np.arange(vc) * (2 * np.pi / vc)
+        verts = np.stack([np.cos(ang), np.sin(ang)], axis=1) * (0.5 + 0.3 * rng.random((vc, 1)))
         lights.append(dict(rotation_angles=angles_for_normal(normal, rng.uniform(0, 2 * np.pi)),
                            scaling_x=float(side), scaling_y=float(side * rng.uniform(0.7, 1.3)),
                            translation=[float(x) for x in pos],

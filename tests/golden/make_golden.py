@@ -34,6 +34,8 @@ VARIANT_ARGS = {  # compiled variant -> orc.variant keyword arguments
     "ris_ltc_weighted_v3": dict(mis="weighted"),
     "ris_ltc_optimal_v3": dict(mis="optimal"),
     "uni_psa_biased_fast_v5": dict(light_sampling="uniform", technique="projected_solid_angle_biased", mis="power", fast_atan=1, min_vertices=3, max_vertices=5),
+    "ris_psa_v6": dict(technique="projected_solid_angle", min_vertices=6, max_vertices=6),
+    "uni_psa_v7": dict(light_sampling="uniform", technique="projected_solid_angle", min_vertices=3, max_vertices=7),
 }
 
 
@@ -60,7 +62,7 @@ def functions():
     rng = np.random.default_rng(11)
     out = {}
     # clip + LTC integral + PSA per compiled MAX_POLYGON_VERTEX_COUNT (P = V_max + 1)
-    for name, n_lo, n_hi in (("ris_ltc_v3", 3, 3), ("ris_ltc_v4", 4, 4), ("uni_psa_biased_fast_v5", 3, 5)):
+    for name, n_lo, n_hi in (("ris_ltc_v3", 3, 3), ("ris_ltc_v4", 4, 4), ("uni_psa_biased_fast_v5", 3, 5), ("uni_psa_v7", 3, 7)):
         r = ref.RefShading(name)
         polys, counts = random_polygons(rng, 400, n_lo, n_hi)
         clipped = np.zeros_like(polys); vcs = np.zeros(len(counts), dtype=np.uint32); ltc = np.zeros(len(counts), dtype=np.float32)
@@ -126,11 +128,14 @@ def frames():
     fits = ltc_fit.fit_ggx_ltc(16, 6, 16)
     rgba, rg = ltc_fit.quantize_fits(fits)
     out = {"ltc.rgba16": rgba, "ltc.rg16": rg}
-    for verts in (3, 4, 5):
+    for verts in (3, 4, 5, 6, 7):
         scene = scenes.many_light_room(12, 10, seed=3, width=W, height=H, vertex_count=verts)
         if verts == 5:   # mixed vertex counts (MIN < MAX)
             for l in scene["lights"][::2]:
                 l["vertices_plane_space"] = l["vertices_plane_space"][:3]
+        if verts == 7:   # every count from 3 to 7
+            for i, l in enumerate(scene["lights"]):
+                l["vertices_plane_space"] = l["vertices_plane_space"][:3 + i % 5]
         osc = orc.OracleScene(scene, rgba, rg)
         cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=16, ltc_layers=6) for f in range(F)]
         k = f"scene_v{verts}"

@@ -5,18 +5,32 @@ Two modes are checked (include/risltc_cuda.h, risltc_cuda_set_precision):
   fast  -- the production mode: the persistent fused kernel whose 32-candidate loop uses fused multiply-adds and MUFU
            rsqrt / rcp; the winner's estimator stays exactly rounded.
 Tolerance (BASELINE.json north_star): relative RMSE <= 1e-3 on the converged (accumulated) frame and >= 99 % of the
-pixels of a frame agreeing, where a pixel agrees iff |a - b| <= 1e-3 max(|a|, |b|) + 1e-5 on every channel
-of the fp32 accumulation buffer. Per-pixel agreement is gated per frame (1 spp each, the reference's own sample unit):
-the shading algorithm is ill-conditioned for small solid angles (differences of atan terms), so that even the
-reference's GLSL compiled with FMA contraction agrees with its uncontracted self on only 99.3 % / 98.6 % / 97.9 % of the
-pixels after 1 / 4 / 16 accumulated frames at this threshold ("noise floor"); for accumulated frames the
-agreement is printed and gated against that control."""
+pixels agreeing AT MATCHED SPP (1, 4 and 16 accumulated frames alike), where a pixel agrees iff
+|a - b| <= 1e-3 max(|a|, |b|) + 1e-5 on every channel of the fp32 accumulation buffer. Both modes are
+gated at that tolerance or tighter (GATES below); every figure is also appended to gpurun_out/parity_log.txt, which is
+committed under profiles/ after a GPU session."""
 import numpy as np
 import pytest
 
-from tests.util import constants_bytes, image_metrics, setup_device
+from tests.util import constants_bytes, image_metrics, parity_log, setup_device
 
 pytestmark = pytest.mark.gpu
+
+# minimal per-pixel agreement and maximal relative RMSE of a CONVERGED frame (>= 16 spp) per mode. A frame of 1-4 spp is not
+# converged: one reservoir decision flipped by a rounding replaces a pixel's whole sample, which moves the frame's RMSE by
+# more than 1e-3 while touching a single pixel; such frames are gated at RMSE_UNCONVERGED (the agreement gate is the same).
+GATES = {"exact": dict(agree=0.999, rmse=1e-3), "fast": dict(agree=0.99, rmse=1e-3)}
+RMSE_UNCONVERGED = 5e-2
+
+
+def check(tag, precision, got, ref, frames, counters=None, ref_rays=None, agree_floor=None):
+    rmse, agree = image_metrics(got, ref)
+    extra = "" if counters is None else f" rays gpu={counters['shadow_rays']} cpu={ref_rays}"
+    parity_log(f"{tag} [{precision}, {frames} spp]: rel_rmse={rmse:.3e} agree={agree:.5f}{extra}")
+    gate = GATES[precision]
+    assert agree >= (gate["agree"] if agree_floor is None else agree_floor), f"{tag}: pixel agreement {agree:.5f}"
+    assert rmse <= (gate["rmse"] if frames >= 16 else RMSE_UNCONVERGED), f"{tag}: relative RMSE {rmse:.3e}"
+    return rmse, agree
 
 
 def _render_both(device, scene, ltc_tables, ovar, gvar, width, height, frames, precision="exact", **ckw):
@@ -43,9 +57,8 @@ def test_quad_over_plane(device, ltc_tables, light_sampling, technique, precisio
     kw = dict(light_sampling=light_sampling, technique=technique, min_vertices=4, max_vertices=4)
     ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 320, 180, 1, precision)
     assert np.array_equal(vis, ref_vis), "primary visibility must be bit-exact"
-    rmse, agree = image_metrics(got, ref)
-    print(f"quad {light_sampling}/{technique}/{precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
-    assert rmse <= 1e-3 and agree >= 0.99
+    rmse, _ = check(f"quad over plane {light_sampling}/{technique}", precision, got, ref, 1, counters, ref_rays)
+    assert rmse <= 1e-3
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
@@ -57,13 +70,7 @@ def test_room_default_variant(device, ltc_tables, frames, precision):
     scene = scenes.many_light_room(64, 50, width=320, height=180)
     ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), 320, 180, frames, precision)
     assert np.array_equal(vis, ref_vis), "primary visibility must be bit-exact"
-    rmse, agree = image_metrics(got, ref)
-    print(f"room frames={frames} {precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
-    # reference-vs-contracted-reference control at this threshold: 0.993 / 0.986 / 0.979 after 1 / 4 / 16 frames
-    assert agree >= {1: 0.99, 4: 0.986, 16: 0.979}[frames]
-    # a single flipped reservoir decision changes one pixel of a 1-spp frame completely; the RMSE bound of
-    # BASELINE.json is for the converged (accumulated) frame
-    assert rmse <= (1e-3 if frames >= 16 else 5e-2)
+    check("room 64 lights 320x180, default estimator", precision, got, ref, frames, counters, ref_rays)
     assert counters["candidates"] == 32 * counters["shaded_pixels"]
 
 
@@ -77,6 +84,10 @@ VARIANTS = [
     dict(mis="optimal"),
     dict(mis="power", technique="projected_solid_angle_biased", fast_atan=1),
     dict(min_vertices=4, max_vertices=4),
+    dict(min_vertices=5, max_vertices=5),
+    dict(technique="projected_solid_angle", min_vertices=6, max_vertices=6),
+    dict(light_sampling="uniform", technique="projected_solid_angle", min_vertices=3, max_vertices=7),
+    dict(min_vertices=3, max_vertices=7),
 ]
 
 
@@ -86,15 +97,70 @@ def test_room_variants(device, ltc_tables, kw, precision):
     """The other shader variants of the comparison matrix (experiment_list.c:316-396)."""
     from oracle import orc
     from risltc_b200 import api, scenes
-    verts = kw.get("max_vertices", 3)
-    scene = scenes.many_light_room(24, 30, seed=4, width=256, height=144, vertex_count=verts)
+    lo, hi = kw.get("min_vertices", 3), kw.get("max_vertices", 3)
+    scene = scenes.many_light_room(24, 30, seed=4, width=256, height=144, vertex_count=hi if lo == hi else (lo, hi))
     ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 256, 144, 2, precision)
     assert np.array_equal(vis, ref_vis)
-    rmse, agree = image_metrics(got, ref)
-    print(f"variant {kw} {precision}: rel_rmse={rmse:.3e} agree={agree:.5f} rays gpu={counters['shadow_rays']} cpu={ref_rays}")
-    # PSA as the RIS target function makes the reservoir itself depend on differences of atan terms: libm ulps flip choices
-    psa_target = "projected_solid_angle" in kw.get("technique", "") and kw.get("light_sampling", "reservoir") == "reservoir"
-    assert agree >= (0.97 if psa_target else 0.99) and rmse <= 5e-2
+    check("variant " + " ".join(f"{a}={b}" for a, b in kw.items()), precision, got, ref, 2, counters, ref_rays)
+
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+@pytest.mark.parametrize("lights", [1024, 4096])
+def test_many_lights(device, ltc_tables, lights, precision):
+    """BASELINE.json configs[2] / [4] light counts against the oracle: 1024 lights is C3's table (the persistent RIS kernel
+    then runs 22-warp CTAs beside a 48 KB table in shared memory), 4096 lights exceeds the shared-memory table and takes
+    the kernel's global-memory instantiation (shade_fast.cuh, ris_ltc3_kernel<false>); shading_pass.frag.glsl:723-761."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    scene = scenes.many_light_room(lights, 60, seed=8, width=320, height=180)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), 320, 180, 4, precision)
+    assert np.array_equal(vis, ref_vis)
+    check(f"room {lights} lights 320x180, default estimator", precision, got, ref, 4, counters, ref_rays)
+    assert counters["candidates"] == 32 * counters["shaded_pixels"]
+
+
+@pytest.mark.parametrize("precision", ["fast", "exact"])
+def test_c2_full_size_against_compiled_reference(device, precision):
+    """BASELINE.json configs[1] at its real size (1920x1080, 64 lights, the bench's scene and 64 x 64 x 51 LTC tables), two
+    accumulated frames, against the REFERENCE's own shading_pass.frag.glsl compiled for the CPU (oracle/_ref) where that
+    library travelled with the snapshot, else against the oracle (which is pinned bit for bit to it)."""
+    from oracle import orc, ref
+    from risltc_b200 import api, ltc_fit, scenes
+    W, H, frames = 1920, 1080, 2
+    rgba, rg = ltc_fit.quantize_fits(ltc_fit.fit_ggx_ltc(64, 51, 64))
+    scene = scenes.many_light_room(64, 200, seed=2, width=W, height=H)
+    osc = orc.OracleScene(scene, rgba, rg)
+    cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0]) for f in range(frames)]
+    if ref.available("ris_ltc_v3"):
+        r = ref.RefShading("ris_ltc_v3"); r.bind(osc)
+        want, want_vis, want_rays = r.render(cs)
+        checker = "compiled reference GLSL"
+    else:
+        want, want_vis, want_rays = osc.render(cs, orc.variant())
+        checker = "oracle"
+    setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records)
+    device.set_precision(precision)
+    device.render_frames(constants_bytes(cs))
+    got, vis, counters = device.read_accum(), device.read_visibility(), device.counters()
+    assert np.array_equal(vis, want_vis), "primary visibility must be bit-exact at full size"
+    check(f"C2 full size 1920x1080 vs {checker}", precision, got, want, frames, counters, want_rays)
+
+
+@pytest.mark.parametrize("precision", ["fast", "exact"])
+def test_c4_shaped_scene(device, ltc_tables, precision):
+    """BASELINE.json configs[3] in shape: 64 lights over a field of 1.1 M occluder triangles. Beyond the rasteriser's queue of
+    2^20 triangles the visibility pass is the per-pixel BVH walk (api.cu), the trees are ~25 levels deep and most shadow
+    rays are occluded. Visibility bit-exact, image within tolerance, ray counts close."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    W, H, frames = 480, 270, 2
+    scene = scenes.many_light_room(64, 200, seed=2, occluder_triangles=1_100_000, width=W, height=H)
+    assert scene["mesh"]["material_indices"].shape[0] > (1 << 20)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), W, H, frames, precision)
+    assert np.array_equal(vis, ref_vis), "primary visibility must be bit-exact"
+    check("C4-shaped scene, 1.1 M triangles, 480x270", precision, got, ref, frames, counters, ref_rays)
+    assert abs(counters["shadow_rays"] - ref_rays) <= max(16, ref_rays // 2000)
 
 
 @pytest.mark.parametrize("precision", ["exact", "fast"])
@@ -194,7 +260,7 @@ def test_full_size_properties(device, ltc_tables):
         assert np.all(np.isfinite(a))
         images[precision] = a
     rmse, agree = image_metrics(images["fast"], images["exact"])
-    print(f"1920x1080 fast vs exact, 3 frames: rel_rmse={rmse:.3e} agree={agree:.5f}")
+    parity_log(f"1920x1080 fast vs exact, 3 frames: rel_rmse={rmse:.3e} agree={agree:.5f}")
     assert agree >= 0.99
 
 
@@ -235,9 +301,7 @@ def test_host_layer_path_equals_direct_path(ltc_tables, tmp_path):
     diff = [i for i in range(256) if consts_before[i] != want[i]]
     assert not diff, f"write_constants differs from the oracle's block at bytes {diff}"
     ref, _, _ = osc.render(cs, orc.variant())
-    rmse, agree = image_metrics(got, ref)
-    print(f"host layer path: rel_rmse={rmse:.3e} agree={agree:.5f}")
-    assert agree >= 0.99
+    check("host layer path 160x90", "fast", got, ref, 2)
 
 
 def C_string(c):

@@ -26,7 +26,7 @@ def _bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-@pytest.mark.parametrize("name,vmin,P,fast,biased", [("ris_ltc_v3", 3, 4, 0, 0), ("ris_ltc_v4", 4, 5, 0, 0), ("uni_psa_biased_fast_v5", 3, 6, 1, 1)])
+@pytest.mark.parametrize("name,vmin,P,fast,biased", [("ris_ltc_v3", 3, 4, 0, 0), ("ris_ltc_v4", 4, 5, 0, 0), ("uni_psa_biased_fast_v5", 3, 6, 1, 1), ("uni_psa_v7", 3, 8, 0, 0)])
 def test_polygon_functions(fn, name, vmin, P, fast, biased):
     polys, counts = fn[f"{name}.polygons"], fn[f"{name}.counts"]
     checked_ltc = 0
@@ -50,7 +50,7 @@ def test_polygon_functions(fn, name, vmin, P, fast, biased):
             want_poly[35 + vc - 1] = 0.0; poly[35 + vc - 1] = 0.0
         assert np.array_equal(_bits(poly), _bits(want_poly)), f"prepared polygon {i}"
         assert np.array_equal(_bits(d), _bits(fn[f"{name}.psa_dir"][i])), f"sampled direction {i}"
-    if name != "uni_psa_biased_fast_v5":
+    if name in ("ris_ltc_v3", "ris_ltc_v4"):
         assert checked_ltc > 50
 
 
@@ -97,6 +97,8 @@ FRAME_VARIANTS = {
     "ris_psa_s2l2_v3": dict(technique="projected_solid_angle", mis="balance", sample_count=2, light_samples=2),
     "ris_ltc_weighted_v3": dict(mis="weighted"), "ris_ltc_optimal_v3": dict(mis="optimal"),
     "uni_psa_biased_fast_v5": dict(light_sampling="uniform", technique="projected_solid_angle_biased", mis="power", fast_atan=1, min_vertices=3, max_vertices=5),
+    "ris_psa_v6": dict(technique="projected_solid_angle", min_vertices=6, max_vertices=6),
+    "uni_psa_v7": dict(light_sampling="uniform", technique="projected_solid_angle", min_vertices=3, max_vertices=7),
 }
 
 

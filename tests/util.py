@@ -25,3 +25,17 @@ def setup_device(dev, scene, rgba, rg, var, width, height, records, stripes=(8, 
 def constants_bytes(constants_list):
     import ctypes
     return b"".join(bytes(ctypes.string_at(ctypes.byref(c), 256)) for c in constants_list)
+
+
+def parity_log(line):
+    """Print a parity figure and append it to gpurun_out/parity_log.txt (copied to profiles/ after a GPU session, so that
+    the numbers behind the gates are committed, not only their pass / fail)."""
+    from pathlib import Path
+    print(line)
+    out = Path(__file__).resolve().parent.parent / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_log.txt", "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass

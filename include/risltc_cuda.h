@@ -136,6 +136,15 @@ int risltc_cuda_owned_row_indices(const risltc_device_t* device, uint32_t* rows)
  * over the frames of the call (CUDA events on the device's stream around every launch), and the whole call. */
 float risltc_cuda_last_frame_ms(risltc_device_t* device);
 int risltc_cuda_last_kernel_ms(risltc_device_t* device, float ms[4]);
+/* The five passes of the last call separately: ms[6] = visibility (1), RIS candidates (2a), winner's estimator (2b), shadow
+ * rays (3), MIS sum + accumulation (4), each summed over the frames of the call, and the whole call. Variants that run
+ * the generic kernel report all of (2) in ms[1]. With frame overlap on the intervals of consecutive frames overlap. */
+int risltc_cuda_last_pass_ms(risltc_device_t* device, float ms[6]);
+/* Traversal statistics of the shadow-ray kernel (bytes per ray from traversal counters). `enable` != 0
+ * switches the kernel to its counting instantiation for the following calls; `counters` (may be NULL) receives those of
+ * the last render call that ran with counting on: rays traced, 4-wide nodes visited (64 B each), triangles tested (48 B
+ * each), rays found occluded. Counting costs a few percent; it is off by default. */
+int risltc_cuda_traversal_counters(risltc_device_t* device, uint32_t enable, uint64_t counters[4]);
 /* Counters of the last frame: [0] covered (non-background) pixel-samples, [1] shadow rays traced,
  * [2] kernels launched since create, [3] RIS candidates evaluated. */
 int risltc_cuda_counters(risltc_device_t* device, uint64_t counters[4]);

@@ -162,6 +162,18 @@ class Device:
         _check(lib().risltc_cuda_last_kernel_ms(self.h, ms))
         return list(ms)
 
+    def last_pass_ms(self):
+        """[visibility, RIS, winner, shadow rays, accumulation, whole call] in ms, summed over the frames of the last call."""
+        ms = (C.c_float * 6)()
+        _check(lib().risltc_cuda_last_pass_ms(self.h, ms))
+        return list(ms)
+
+    def traversal_counters(self, enable=True):
+        """Counters of the last counted call (rays, node visits, triangle tests, occluded rays); switches counting on / off."""
+        c = (C.c_uint64 * 4)()
+        _check(lib().risltc_cuda_traversal_counters(self.h, C.c_uint32(int(enable)), c))
+        return dict(rays=int(c[0]), node_visits=int(c[1]), triangle_tests=int(c[2]), occluded=int(c[3]))
+
     def counters(self):
         c = (C.c_uint64 * 4)()
         _check(lib().risltc_cuda_counters(self.h, c))

@@ -24,6 +24,8 @@ int rl_fail(const char* what, const char* detail) {
 }
 #define fail rl_fail
 
+#define RL_FRAME_EVENTS 6
+
 struct risltc_device_s {
 	int ordinal = 0;
 	cudaStream_t stream = nullptr;
@@ -66,11 +68,12 @@ struct risltc_device_s {
 	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (768: 80 registers; 512: 117, slower)
 	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel (128, 256 or 384; measured best: 384)
+	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
 	unsigned long long launches = 0;
 	bool timed = false;
-	// per-frame events of the last batch: 4 per frame (before (1), after (1), after (2), after (3+4))
+	// per-frame events of the last batch: RL_FRAME_EVENTS per frame (before (1), after (1), after (2a), after (2b) = after (2), after (3), after (4))
 	std::vector<cudaEvent_t> frame_events;
 	uint32_t timed_frames = 0;
 };
@@ -107,8 +110,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	d->sm_count = prop.multiProcessorCount;
-	CU(cudaMalloc(&d->px.counters, 4 * sizeof(unsigned long long)));
-	CU(cudaMemset(d->px.counters, 0, 4 * sizeof(unsigned long long)));
+	CU(cudaMalloc(&d->px.counters, 8 * sizeof(unsigned long long)));
+	CU(cudaMemset(d->px.counters, 0, 8 * sizeof(unsigned long long)));
 	CU(cudaMalloc(&d->px.ticket, 4 * sizeof(unsigned int)));
 	CU(cudaMemset(d->px.ticket, 0, 4 * sizeof(unsigned int)));
 	// rasteriser: item queue, {counter, ticket} in one 16-byte block
@@ -116,7 +119,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaMalloc(&d->raster.counter, 16));
 	d->raster.ticket = (unsigned int*) (d->raster.counter + 1);
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
-	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel, 128, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
 	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { d->winner_resident = (atoi(e) == 512) ? 512u : 768u; if (d->winner_resident == 512) d->winner_threads = 256; }
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 128 || t == 256) ? (uint32_t) t : 384u; }
@@ -449,7 +452,7 @@ static const uint32_t kMaxSmemLights = 2048;
 
 // (2): the specialised persistent kernel of shade_fast.cuh when the variant is the default estimator on triangle
 // lights and the device is in RISLTC_PRECISION_FAST, the generic kernel otherwise.
-static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, const PixelBuffers& px, cudaStream_t stream) {
+static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, const PixelBuffers& px, cudaStream_t stream, cudaEvent_t between) {
 	const Variant& v = d->variant;
 	const bool defer = deferred_rays(v);
 	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
@@ -479,7 +482,10 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		}
 		d->launches += 1;
 	}
-	else return rl_launch_generic_shade(d->view, f, v, d->stripes, px, grid, defer, stream);
+	else {
+		if (rl_launch_generic_shade(d->view, f, v, d->stripes, px, grid, defer, stream)) return 1;
+		CU(cudaEventRecord(between, stream));
+	}
 	return 0;
 }
 
@@ -490,10 +496,10 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 	if (!d->px.pixel_count) return fail("render_frames: call resize first", nullptr);
 	if (d->view.light_stride4 != 3 + d->variant.max_light_vertices) return fail("render_frames: light buffer stride does not match the variant's max_light_vertices", nullptr);
 	dim3 grid((d->width + 15) / 16, (d->stripes.owned_rows + 7) / 8);
-	CU(cudaMemsetAsync(d->px.counters, 0, 4 * sizeof(unsigned long long), d->stream));
+	CU(cudaMemsetAsync(d->px.counters, 0, 8 * sizeof(unsigned long long), d->stream));
 	CU(cudaMemsetAsync(d->px.ticket, 0, 4 * sizeof(unsigned int), d->stream));
 	if (d->set2_ready) CU(cudaMemsetAsync(d->px2.ticket, 0, 4 * sizeof(unsigned int), d->stream));   // a failed call must not leave tickets behind
-	while (d->frame_events.size() < 4 * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
+	while (d->frame_events.size() < RL_FRAME_EVENTS * (size_t) frame_count) { cudaEvent_t e; CU(cudaEventCreate(&e)); d->frame_events.push_back(e); }
 	d->timed_frames = frame_count;
 	CU(cudaEventRecord(d->ev[0], d->stream));
 	const bool overlap = d->overlap && frame_count >= 2;
@@ -516,7 +522,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		cudaStream_t stream = set ? d->stream2 : d->stream;
 		used_second |= set != 0;
 		d->last_set = set;
-		cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
+		cudaEvent_t* fe = &d->frame_events[RL_FRAME_EVENTS * (size_t) i];
 		CU(cudaEventRecord(fe[0], stream));
 		uint32_t kind = d->gbuffer_kind;
 		if (d->gbuffer_tune < 3) {
@@ -544,23 +550,25 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		else gbuffer_kernel<<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);
 		if (d->gbuffer_tune < 2) { CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune + 1], stream)); d->gbuffer_tune++; }
 		CU(cudaEventRecord(fe[1], stream));
-		if (launch_shade(d, grid, f, px, stream)) return 1;
-		CU(cudaEventRecord(fe[2], stream));
+		if (launch_shade(d, grid, f, px, stream, fe[2])) return 1;
+		CU(cudaEventRecord(fe[3], stream));
 		const bool traced = d->precision == RISLTC_PRECISION_FAST && deferred_rays(d->variant);
 		if (traced) {
 			// (3) persistent any-hit traversal over all ray slots
 			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
 			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < d->trace4_resident) ? d->trace_ctas_per_sm : d->trace4_resident;
-			if (d->trace_kind == 4) trace4_kernel<<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
+			if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
+			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
 			d->launches += 1;
 		}
+		CU(cudaEventRecord(fe[4], stream));
 		// (4) MIS sum + accumulation: the running mean takes the frames in order, whichever stream they were rendered on
 		if (overlap && i != 0) CU(cudaStreamWaitEvent(stream, d->ev_resolved[(i - 1) & 1u], 0));
 		if (traced) resolve_kernel<true><<<grid, 128, 0, stream>>>(d->view, f, d->variant, d->stripes, px);
 		else resolve_kernel<false><<<grid, 128, 0, stream>>>(d->view, f, d->variant, d->stripes, px);
 		if (overlap) CU(cudaEventRecord(d->ev_resolved[i & 1u], stream));
-		CU(cudaEventRecord(fe[3], stream));
+		CU(cudaEventRecord(fe[5], stream));
 		d->launches += 3;
 	}
 	if (used_second) {
@@ -605,16 +613,23 @@ extern "C" float risltc_cuda_last_frame_ms(risltc_device_t* d) {
 	return ms[3];
 }
 
-extern "C" int risltc_cuda_last_kernel_ms(risltc_device_t* d, float ms[4]) {
+extern "C" int risltc_cuda_last_pass_ms(risltc_device_t* d, float ms[6]) {
 	if (use(d)) return 1;
-	if (!d->timed) return fail("last_kernel_ms: no frame rendered yet", nullptr);
+	if (!d->timed) return fail("last_pass_ms: no frame rendered yet", nullptr);
 	CU(cudaEventSynchronize(d->ev[4]));
-	ms[0] = ms[1] = ms[2] = 0.0f;
+	for (int k = 0; k != 5; ++k) ms[k] = 0.0f;
 	for (uint32_t i = 0; i != d->timed_frames; ++i) {
-		const cudaEvent_t* fe = &d->frame_events[4 * (size_t) i];
-		for (int k = 0; k != 3; ++k) { float t = 0.0f; CU(cudaEventElapsedTime(&t, fe[k], fe[k + 1])); ms[k] += t; }
+		const cudaEvent_t* fe = &d->frame_events[RL_FRAME_EVENTS * (size_t) i];
+		for (int k = 0; k != 5; ++k) { float t = 0.0f; CU(cudaEventElapsedTime(&t, fe[k], fe[k + 1])); ms[k] += t; }
 	}
-	CU(cudaEventElapsedTime(&ms[3], d->ev[0], d->ev[4]));
+	CU(cudaEventElapsedTime(&ms[5], d->ev[0], d->ev[4]));
+	return 0;
+}
+
+extern "C" int risltc_cuda_last_kernel_ms(risltc_device_t* d, float ms[4]) {
+	float pass[6];
+	if (risltc_cuda_last_pass_ms(d, pass)) return 1;
+	ms[0] = pass[0]; ms[1] = pass[1] + pass[2]; ms[2] = pass[3] + pass[4]; ms[3] = pass[5];
 	return 0;
 }
 
@@ -624,6 +639,18 @@ extern "C" int risltc_cuda_counters(risltc_device_t* d, uint64_t counters[4]) {
 	CU(cudaMemcpyAsync(h, d->px.counters, sizeof(h), cudaMemcpyDeviceToHost, d->stream));
 	CU(cudaStreamSynchronize(d->stream));
 	counters[0] = h[0]; counters[1] = h[1]; counters[2] = d->launches; counters[3] = h[3];
+	return 0;
+}
+
+extern "C" int risltc_cuda_traversal_counters(risltc_device_t* d, uint32_t enable, uint64_t counters[4]) {
+	if (use(d)) return 1;
+	CU(cudaStreamSynchronize(d->stream));
+	if (counters) {
+		unsigned long long h[4];
+		CU(cudaMemcpy(h, d->px.counters + 4, sizeof(h), cudaMemcpyDeviceToHost));
+		for (int i = 0; i != 4; ++i) counters[i] = h[i];
+	}
+	d->count_traversal = enable != 0;
 	return 0;
 }
 
@@ -730,7 +757,7 @@ extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint
 	PixelBuffers px = {};
 	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
 	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
-	if (kind == 4) trace4_kernel<<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
+	if (kind == 4) trace4_kernel<false><<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
 	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
 	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
 	CU(cudaDeviceSynchronize());

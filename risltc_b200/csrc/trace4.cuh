@@ -27,6 +27,9 @@ __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm(
 // plane byte k of `word` -> float 1 + q * 2^-15
 __device__ __forceinline__ float q4_plane(uint32_t word, uint32_t selector) { return __uint_as_float(__byte_perm(word, 0x3F800000u, selector)); }
 
+// COUNT = true additionally counts the rays, node visits, triangle tests and occluded rays of the launch into
+// px.counters[4..7] (bench.py's roofline_trace block: bytes per ray); the frame path runs COUNT = false unless asked.
+template <bool COUNT>
 __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote, uint32_t refill) {
 	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
 	__shared__ int sm_nstack[RL_T4_NSTACK][128];
@@ -42,6 +45,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 	int node = -1, nsp = 0, lsp = 0, spilled = 0;
 	const float t_min = 1.0e-3f;
 	uint32_t ahead = 0;
+	uint32_t n_rays = 0, n_nodes = 0, n_tris = 0, n_occluded = 0;
 	if (lane == 0) ahead = atomicAdd(px.ticket, RL_TRACE_STAGE);
 	ahead = __shfl_sync(0xFFFFFFFFu, ahead, 0);
 	while (true) {
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 		// ---- track A: one node = four child boxes. No divergent branches: every child stores its reference to the top of
 		// both stacks and CLAIMS the slot only if it belongs there; the last inner hit stays in a register as the next node.
 		if (node_ready) {
+			if (COUNT) ++n_nodes;
 			const Qbvh4Node* np = s.nodes4 + node;
 			const uint4 na = __ldg(&np->a), nb = __ldg(&np->b), nc = __ldg(&np->c);
 			const int4 refs = __ldg(&np->refs);
@@ -154,13 +159,23 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 				const uint32_t ref = ~(uint32_t) sm_lstack[--lsp][tid];
 				tri_i = ref >> 4; tri_end = tri_i + (ref & 15u) + 1u;
 			}
+			if (COUNT) ++n_tris;
 			if (tri_any_hit(s.tris[tri_i], o, d, t_min, t_max)) {
 				((float*) px.ray_b)[4 * (size_t) ray + 3] = 2.0f;
 				busy = false;
+				if (COUNT) ++n_occluded;
 			}
 			++tri_i;
 		}
 		if (busy && node < 0 && tri_i == tri_end && lsp == 0) busy = false;   // nothing left on either track: the ray reaches the light
+	}
+	if (COUNT) {
+		n_rays = __reduce_add_sync(0xFFFFFFFFu, n_rays); n_nodes = __reduce_add_sync(0xFFFFFFFFu, n_nodes);
+		n_tris = __reduce_add_sync(0xFFFFFFFFu, n_tris); n_occluded = __reduce_add_sync(0xFFFFFFFFu, n_occluded);
+		if (lane == 0) {
+			atomicAdd(&px.counters[4], (unsigned long long) n_rays); atomicAdd(&px.counters[5], (unsigned long long) n_nodes);
+			atomicAdd(&px.counters[6], (unsigned long long) n_tris); atomicAdd(&px.counters[7], (unsigned long long) n_occluded);
+		}
 	}
 }
 

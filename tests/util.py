@@ -30,7 +30,10 @@ def constants_bytes(constants_list):
 def parity_log(line):
     """Print a parity figure and append it to gpurun_out/parity_log.txt (copied to profiles/ after a GPU session, so that
     the numbers behind the gates are committed, not only their pass / fail)."""
+    import os
     from pathlib import Path
+    if os.environ.get("RISLTC_WINNER"):
+        line = f"[RISLTC_WINNER={os.environ['RISLTC_WINNER']}] " + line
     print(line)
     out = Path(__file__).resolve().parent.parent / "gpurun_out"
     try:

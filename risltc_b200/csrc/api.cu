@@ -1,4 +1,5 @@
 // api.cu -- C ABI of librisltc_cuda.so (include/risltc_cuda.h) and kernel launches.
+#define RL_PSA_ATTR __forceinline__   // the production kernels call the PSA functions once per loop body (shading.cuh)
 #include "internal.h"
 #include "kernels.cuh"
 #include "shade_fast.cuh"
@@ -65,9 +66,8 @@ struct risltc_device_s {
 	cudaEvent_t tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
-	uint32_t winner_resident = 768;  // threads of the winner kernel resident per SM (768: 80 registers; 512: 117, slower)
 	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
-	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel (128, 256 or 384; measured best: 384)
+	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel, two CTAs per SM: 384 (80 registers), 320 (96) or 256 (128)
 	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
 	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
@@ -121,8 +121,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
-	if (const char* e = getenv("RISLTC_WIN_RESIDENT")) { d->winner_resident = (atoi(e) == 512) ? 512u : 768u; if (d->winner_resident == 512) d->winner_threads = 256; }
-	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 128 || t == 256) ? (uint32_t) t : 384u; }
+	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 256 || t == 320) ? (uint32_t) t : 384u; }
 	if (const char* e = getenv("RISLTC_WINNER")) d->winner_cr = strcmp(e, "cr") == 0;
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
 	for (auto& ev : d->tune_ev) CU(cudaEventCreate(&ev));
@@ -469,15 +468,15 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
 		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		CU(cudaEventRecord(between, stream));
 		{
 			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles
-			const uint32_t threads = (d->winner_resident == 512) ? 256u : d->winner_threads, per_cta = threads / 32;
-			uint32_t wctas = (d->winner_resident / threads) * (uint32_t) d->sm_count;
+			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
+			uint32_t wctas = 2u * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
 			if (d->winner_cr) { if (rl_launch_winner_cr(d->view, f, d->stripes, px, tiles_x, tile_count, std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), stream)) return 1; }
-			else if (d->winner_resident == 512) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 128) winner_kernel<128, 768><<<wctas, 128, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 256) winner_kernel<256, 768><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 320) winner_kernel<320, 640><<<wctas, 320, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		}
 		d->launches += 1;

@@ -269,23 +269,49 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 	}
 }
 
+// clip_to_horizon<4> for a triangle (vertex count == MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING == 3) without the dynamically
+// indexed walk: the same vertices in the same order (polygon_clipping.glsl:56-75: row 0 of the rotation table), every slot
+// addressed statically so that the polygon stays in registers. horizon_crossing(v_i, v_i+1) per crossed edge, as there.
+__device__ __forceinline__ uint32_t clip_triangle_to_horizon(float3 (&v)[4]) {
+	const uint32_t mask = (v[0].z > 0.0f ? 1u : 0u) | (v[1].z > 0.0f ? 2u : 0u) | (v[2].z > 0.0f ? 4u : 0u);
+	if (mask == 0u) return 0u;
+	if (mask == 7u) return 3u;
+	const float3 a = v[0], b = v[1], c = v[2];
+	switch (mask) {
+	case 1u: v[1] = horizon_crossing(a, b); v[2] = horizon_crossing(c, a); return 3u;            // v0, x01, x20
+	case 2u: v[0] = horizon_crossing(a, b); v[2] = horizon_crossing(b, c); return 3u;            // x01, v1, x12
+	case 3u: v[2] = horizon_crossing(b, c); v[3] = horizon_crossing(c, a); return 4u;            // v0, v1, x12, x20
+	case 4u: v[0] = horizon_crossing(c, a); v[1] = horizon_crossing(b, c); return 3u;            // x20, x12, v2 (walk rotated by 2)
+	case 5u: v[1] = horizon_crossing(a, b); v[2] = horizon_crossing(b, c); v[3] = c; return 4u;  // v0, x01, x12, v2
+	default: v[0] = horizon_crossing(a, b); v[3] = horizon_crossing(c, a); return 4u;            // 6: x01, v1, v2, x20
+	}
+}
+
 // The winner's estimator (evaluate_polygonal_light_shading_peters, shading_pass.frag.glsl:292-397) for the light that
 // ris_ltc3_kernel chose; shadow rays are deferred to the trace kernel. Every operation here is rounded as in the oracle.
 //
-// Organisation: the estimator is ~80 KB of straight-line SASS, far beyond the 32 KB instruction cache of an SM, and ncu
-// showed the first version (one pixel per thread, 128-thread CTAs running through it at their own pace) stalled on
-// instruction fetch (no_instruction 3.8 warps per issue, issue-active 47 %). Here a CTA of RL_WIN_THREADS walks through
-// the estimator in PHASES separated by __syncthreads(), so that all its warps execute the same < 32 KB of code at the same
-// time and every instruction line is fetched once per CTA and phase instead of once per warp: (A) shading point, LTC frame,
-// light, both clipped polygons; (B) PSA preparation of the diffuse polygon; (C) of the specular polygon (the same code,
-// still cached); (D) diffuse sample; (E) specular sample (same code); (F) densities, BRDF, MIS weights, ray records.
+// Organisation. The estimator is ~80 KB of straight-line SASS, far beyond the 32 KB instruction cache of an SM: a CTA walks
+// through it in PHASES separated by __syncthreads(), so that all its warps execute the same < 32 KB of code at the same time
+// and every instruction line is fetched once per CTA and phase instead of once per warp (ncu, first version without
+// phases: no_instruction 3.8 warps per issue, issue-active 47 %).
+// The two techniques (diffuse: the polygon in shading space, specular: in cosine space) run through the SAME code, a loop
+// of two iterations with {transform + clip + PSA preparation | barrier | sample | barrier} as its body. Only one prepared
+// polygon exists at a time, and it crosses its barrier in SHARED memory (24 words per thread, one column per thread:
+// bank = lane), all slots addressed statically; the per-sample body only needs the two solid angles. The round-1 kernel
+// kept both polygons, both clipped vertex lists and the light in per-thread local memory behind out-of-line calls
+// (496-byte frames x 768 threads = 380 KB per SM, more than L1 holds): ncu showed 48 M + 47 M local sectors per launch and
+// 477 MB of DRAM writes against 232 MB algorithmic (profiles/r1_ncu_final_kernels.txt).
 // The draws keep the reference's order (diffuse pair, then specular pair only if its solid angle is positive).
+#define RL_POLY_WORDS 24   // vc, v[4], e[4], inner0, sector[4], total
 template <int RL_WIN_THREADS, int RL_WIN_RESIDENT_THREADS>
 __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
 	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
 	// a warp owns 8x4 pixel tiles; the CTA takes `warps` neighbouring tiles per round through a ticket (barriers inside)
 	__shared__ uint32_t sm_base;
+	__shared__ float sm_poly[RL_POLY_WORDS][RL_WIN_THREADS];
+	float* const poly = &sm_poly[0][threadIdx.x];
+	#define RL_POLY(k) poly[(k) * RL_WIN_THREADS]
 	while (true) {
 		__syncthreads();
 		if (threadIdx.x == 0) sm_base = atomicAdd(&out.ticket[2], warps);
@@ -303,64 +329,83 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 		uint4 pick = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
 		if (shaded) pick = out.pick[pixel];
 		bool live = shaded && (int) pick.x >= 0;
-		// ---- (A)
+		// ---- (A) shading point, LTC frame, side of the light's plane
 		ShadingPoint sp;
 		LtcFrame ltc;
-		Light<3> light;
-		Techniques<3> t;
-		float3 pv[4], pq[4];
-		uint32_t vc_d = 0, vc_s = 0;
+		TechniqueTerms t;
+		t.flip = false; t.specular_total = 0.0f;
+		const float4* light_record = s.lights + (size_t) (live ? pick.x : 0u) * s.light_stride4;
 		if (shaded) sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
 		if (live) {
 			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
 			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
-			light = load_light<3>(s, pick.x);
-			t.valid = false;
-			t.flip = plane_side(sp.position, light.plane) < 0.0f;
-			t.specular.total = 0.0f;
-			#pragma unroll
-			for (int i = 0; i != 3; ++i) { pv[i] = to_shading_space(ltc, light.v[i], t.flip); pq[i] = to_cosine_space(ltc, light.v[i], t.flip); }
-			pv[3] = pq[3] = mk3(0.0f, 0.0f, 0.0f);
-			vc_d = clip_to_horizon<4>(light.count, pv, var.min_light_vertices);
-			if (vc_d != 0) vc_s = clip_to_horizon<4>(light.count, pq, var.min_light_vertices);
-			live = vc_d != 0;
+			t.flip = plane_side(sp.position, __ldg(light_record + 1)) < 0.0f;
 		}
-		__syncthreads();
-		// ---- (B), (C): prepare_techniques, shading_pass.frag.glsl:296-363
-		if (live) psa_prepare<4>(t.diffuse, vc_d, pv, false);
-		__syncthreads();
-		if (live && vc_s != 0) psa_prepare<4>(t.specular, vc_s, pq, false);
-		if (live) {
-			live = t.diffuse.total != 0.0f;
-			if (live) {
-				const float sw = ltc.albedo * t.specular.total;
-				const float3 da = mk3(fmaxf(sp.diffuse_albedo.x, 0.01f), fmaxf(sp.diffuse_albedo.y, 0.01f), fmaxf(sp.diffuse_albedo.z, 0.01f));
-				t.diffuse_weight = scale3(da, t.diffuse.total);
-				t.rcp_diffuse = 1.0f / t.diffuse.total;
-				t.rcp_specular = 1.0f / t.specular.total;
-				t.specular_weight = mk3(sw, sw, sw);
-				t.valid = true;
+		uint32_t seed = pick.z;
+		float3 dir0 = mk3(0.0f, 0.0f, 0.0f), dir1 = dir0;
+		float total_d = 0.0f, total_s = 0.0f;
+		bool polygon_d = false;   // the diffuse polygon survived the clip (prepare_techniques returns early otherwise, :307-310)
+		// ---- (B), (C) per technique: prepare_techniques + the technique's sample, shading_pass.frag.glsl:296-372
+		#pragma unroll 1
+		for (int tech = 0; tech != 2; ++tech) {
+			__syncthreads();
+			bool prepared = false;
+			if (live && (tech == 0 || polygon_d)) {
+				float3 pv[4];
+				#pragma unroll
+				for (int i = 0; i != 3; ++i) {
+					const float4 w = __ldg(light_record + 3 + i);
+					pv[i] = tech ? to_cosine_space(ltc, mk3(w.x, w.y, w.z), t.flip) : to_shading_space(ltc, mk3(w.x, w.y, w.z), t.flip);
+				}
+				pv[3] = mk3(0.0f, 0.0f, 0.0f);
+				const uint32_t vc = clip_triangle_to_horizon(pv);
+				if (tech == 0) { polygon_d = vc != 0u; live = polygon_d; }
+				if (vc != 0u) {
+					PsaPolygon<4> p;
+					#pragma unroll
+					for (int i = 0; i != 4; ++i) { p.v[i] = mk2(0.0f, 0.0f); p.e[i] = mk2(0.0f, 0.0f); p.sector[i] = 0.0f; }
+					psa_prepare<4>(p, vc, pv, false);
+					if (tech == 0) { total_d = p.total; live = total_d != 0.0f; }
+					else total_s = p.total;
+					prepared = live && (tech == 0 || total_s > 0.0f);
+					if (prepared) {
+						RL_POLY(0) = __uint_as_float(p.vc);
+						#pragma unroll
+						for (int i = 0; i != 4; ++i) {
+							RL_POLY(1 + 2 * i) = p.v[i].x; RL_POLY(2 + 2 * i) = p.v[i].y;
+							RL_POLY(9 + 2 * i) = p.e[i].x; RL_POLY(10 + 2 * i) = p.e[i].y;
+							RL_POLY(19 + i) = p.sector[i];
+						}
+						RL_POLY(17) = p.inner0.x; RL_POLY(18) = p.inner0.y; RL_POLY(23) = p.total;
+					}
+				}
+			}
+			__syncthreads();
+			if (prepared) {
+				PsaPolygon<4> p;
+				p.vc = __float_as_uint(RL_POLY(0));
+				#pragma unroll
+				for (int i = 0; i != 4; ++i) {
+					p.v[i] = mk2(RL_POLY(1 + 2 * i), RL_POLY(2 + 2 * i));
+					p.e[i] = mk2(RL_POLY(9 + 2 * i), RL_POLY(10 + 2 * i));
+					p.sector[i] = RL_POLY(19 + i);
+				}
+				p.inner0 = mk2(RL_POLY(17), RL_POLY(18)); p.total = RL_POLY(23);
+				const float u0 = noise_next(seed), u1 = noise_next(seed);
+				const float3 d = psa_sample<4>(p, u0, u1, false, false);
+				if (tech == 0) dir0 = d;
+				else dir1 = cosine_to_shading_dir(ltc, d);
 			}
 		}
 		__syncthreads();
-		// ---- (D), (E): one sample per technique (SAMPLE_COUNT = 1), shading_pass.frag.glsl:365-372
-		uint32_t seed = pick.z;
-		float3 dir0 = mk3(0.0f, 0.0f, 0.0f), dir1 = dir0;
-		int techniques = 1;
-		if (live) {
-			const float u0 = noise_next(seed), u1 = noise_next(seed);
-			dir0 = psa_sample<4>(t.diffuse, u0, u1, false, false);
-		}
-		__syncthreads();
-		if (live && t.specular.total > 0.0f) {
-			const float u0 = noise_next(seed), u1 = noise_next(seed);
-			dir1 = cosine_to_shading_dir(ltc, psa_sample<4>(t.specular, u0, u1, false, false));
-			techniques = 2;
-		}
-		__syncthreads();
-		// ---- (F): densities, BRDF, MIS (shading_pass.frag.glsl:373-394); the rays are recorded for the trace kernel
+		// ---- (D): densities, BRDF, MIS (shading_pass.frag.glsl:373-394); the rays are recorded for the trace kernel
 		float3 carry = mk3(0.0f, 0.0f, 0.0f);
 		if (live) {
+			Light<3> light;
+			const float4 la = __ldg(light_record), lb = __ldg(light_record + 1);
+			light.radiance = mk3(la.x, la.y, la.z); light.plane = lb; light.count = 3u;
+			technique_weights(t, sp, ltc.albedo, total_d, total_s, light.radiance, false);
+			const int techniques = (total_s > 0.0f) ? 2 : 1;
 			for (int j = 0; j != techniques; ++j) {
 				RayRequest ray; bool side_visible; float3 if_occluded;
 				ray.dir = mk3(0.0f, 0.0f, 1.0f); ray.t_max = -1.0f; ray.if_visible = mk3(0.0f, 0.0f, 0.0f);
@@ -376,6 +421,7 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 			out.origin[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, __uint_as_float(1u));
 		}
 	}
+	#undef RL_POLY
 }
 
 }  // namespace RL_NS

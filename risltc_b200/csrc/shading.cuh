@@ -10,6 +10,12 @@
 #pragma once
 #include "common.cuh"
 
+// psa_prepare / psa_sample are called from many places of the generic kernel (out of line there: one copy of the code); the
+// phase-structured winner kernel calls each exactly once per loop body and wants them inline, with the polygon in registers
+#ifndef RL_PSA_ATTR
+#define RL_PSA_ATTR __noinline__
+#endif
+
 namespace RL_NS {
 
 // rot[n - 3][above_mask]: slot order of the clipped polygon (tools/gen_clip_table.py); statically initialised, so every
@@ -332,7 +338,7 @@ __device__ void psa_sort(PsaPolygon<P>& p) {   // :444-506
 
 // prepare_projected_solid_angle_polygon_sampling, :545-613
 template <int P>
-__device__ __noinline__ void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
+__device__ RL_PSA_ATTR void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
 	p.vc = vc;
 	float2 inner0 = mk2(1.0f, 0.0f);
 	p.v[0] = mk2(v[0].x, v[0].y);
@@ -342,7 +348,10 @@ __device__ __noinline__ void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const fl
 	for (int i = 1; i != P; ++i) {
 		if ((uint32_t) i >= vc) break;
 		p.v[i] = mk2(v[i].x, v[i].y);
-		float2 e = ellipse_from_edge(v[i], v[((uint32_t) i + 1u == vc) ? 0 : i + 1]);
+		// the successor of the last vertex is vertex 0: selected by VALUE between two statically indexed slots (a selected
+		// index would force the array into local memory)
+		const float3 successor = ((uint32_t) i + 1u == vc || i + 1 == P) ? v[0] : v[(i + 1 < P) ? i + 1 : 0];
+		float2 e = ellipse_from_edge(v[i], successor);
 		bool inner = sign_bit(e.x);
 		p.e[i] = inner ? prev : e;
 		inner0 = (sign_bit(prev.x) && !inner) ? prev : inner0;
@@ -360,7 +369,7 @@ __device__ __noinline__ void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const fl
 		#pragma unroll
 		for (int i = 0; i != P; ++i) {
 			if ((uint32_t) i >= vc) break;
-			float2 d0 = p.v[i], d1 = p.v[((uint32_t) i + 1u == vc) ? 0 : i + 1];
+			float2 d0 = p.v[i], d1 = ((uint32_t) i + 1u == vc || i + 1 == P) ? p.v[0] : p.v[(i + 1 < P) ? i + 1 : 0];
 			float rs = ellipse_rsqrt_det(p.e[i]);
 			float det_dirs = fmaxf(+0.0f, dot2(d1, rotate_90(d0)));
 			float edot = rs * dot2(d0, ellipse_transform(p.e[i], d1));
@@ -443,7 +452,7 @@ __device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 i
 
 // sample_projected_solid_angle_polygon, :772-828
 template <int P>
-__device__ __noinline__ float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
+__device__ RL_PSA_ATTR float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
 	float target = u0 * p.total;
 	float2 s, outer = mk2(0.0f, 0.0f), d0 = mk2(0.0f, 0.0f);
 	if (p.inner0.x > 0.0f) {
@@ -574,20 +583,41 @@ __device__ float3 ltc_target(const ShadingPoint& sp, const LtcFrame& ltc, const 
 }
 
 // The "prepare both techniques" block shared by shading_pass.frag.glsl:296-363 and :462-516
-template <int V>
-struct Techniques {
-	PsaPolygon<V + 1> diffuse, specular;
+// what the per-sample body needs of the two prepared techniques (the polygons themselves are only needed to draw the samples)
+struct TechniqueTerms {
 	float3 diffuse_weight, specular_weight;
 	float rcp_diffuse, rcp_specular;
+	float specular_total;   // projected solid angle of the specular polygon (0: single-technique sample)
 	bool flip;
+};
+template <int V>
+struct Techniques : TechniqueTerms {
+	PsaPolygon<V + 1> diffuse, specular;
 	bool valid;
 };
+
+// diffuse / specular weights and reciprocal solid angles from the two totals (shading_pass.frag.glsl:318-336, :347-352)
+__device__ __forceinline__ void technique_weights(TechniqueTerms& t, const ShadingPoint& sp, float ltc_albedo, float diffuse_total, float specular_total, float3 radiance, bool optimal) {
+	float sw = ltc_albedo * specular_total;
+	float3 da = mk3(fmaxf(sp.diffuse_albedo.x, 0.01f), fmaxf(sp.diffuse_albedo.y, 0.01f), fmaxf(sp.diffuse_albedo.z, 0.01f));
+	t.diffuse_weight = scale3(da, diffuse_total);
+	t.rcp_diffuse = 1.0f / diffuse_total;
+	t.rcp_specular = 1.0f / specular_total;
+	t.specular_weight = mk3(sw, sw, sw);
+	t.specular_total = specular_total;
+	if (optimal) {
+		float3 rop = scale3(radiance, RL_INV_PI);
+		t.diffuse_weight = mul3(t.diffuse_weight, rop);
+		t.specular_weight = mul3(t.specular_weight, rop);
+	}
+}
 
 template <int V>
 __device__ void prepare_techniques(Techniques<V>& t, const ShadingPoint& sp, const LtcFrame& ltc, const Light<V>& light, const Variant& var) {
 	t.valid = false;
 	t.flip = plane_side(sp.position, light.plane) < 0.0f;
 	t.specular.total = 0.0f;
+	t.specular_total = 0.0f;
 	bool fast = var.fast_atan != 0;
 	float3 pv[V + 1];
 	#pragma unroll
@@ -601,17 +631,7 @@ __device__ void prepare_techniques(Techniques<V>& t, const ShadingPoint& sp, con
 	vc = clip_to_horizon<V + 1>(light.count, pv, var.min_light_vertices);
 	if (vc != 0) psa_prepare<V + 1>(t.specular, vc, pv, fast);
 	if (t.diffuse.total == 0.0f) return;
-	float sw = ltc.albedo * t.specular.total;
-	float3 da = mk3(fmaxf(sp.diffuse_albedo.x, 0.01f), fmaxf(sp.diffuse_albedo.y, 0.01f), fmaxf(sp.diffuse_albedo.z, 0.01f));
-	t.diffuse_weight = scale3(da, t.diffuse.total);
-	t.rcp_diffuse = 1.0f / t.diffuse.total;
-	t.rcp_specular = 1.0f / t.specular.total;
-	t.specular_weight = mk3(sw, sw, sw);
-	if (var.mis_heuristic == MIS_OPTIMAL) {
-		float3 rop = scale3(light.radiance, RL_INV_PI);
-		t.diffuse_weight = mul3(t.diffuse_weight, rop);
-		t.specular_weight = mul3(t.specular_weight, rop);
-	}
+	technique_weights(t, sp, ltc.albedo, t.diffuse.total, t.specular.total, light.radiance, var.mis_heuristic == MIS_OPTIMAL);
 	t.valid = true;
 }
 
@@ -619,7 +639,7 @@ __device__ void prepare_techniques(Techniques<V>& t, const ShadingPoint& sp, con
 // point where visibility is needed. Returns false when the sample is skipped (dir.z <= 0).
 // side_visible tells whether a shadow ray has to be traced; if_visible / if_occluded are the terms to add.
 template <int V>
-__device__ bool technique_sample(const Techniques<V>& t, const ShadingPoint& sp, const LtcFrame& ltc, const Light<V>& light, const Variant& var,
+__device__ bool technique_sample(const TechniqueTerms& t, const ShadingPoint& sp, const LtcFrame& ltc, const Light<V>& light, const Variant& var,
 	int j, float3 dir, float mis_ve, bool peters, RayRequest& ray, bool& side_visible, float3& if_occluded)
 {
 	if (dir.z <= 0.0f) return false;
@@ -640,7 +660,7 @@ __device__ bool technique_sample(const Techniques<V>& t, const ShadingPoint& sp,
 		ray.t_max = -plane_side(sp.position, light.plane) / (w.x * light.plane.x + w.y * light.plane.y + w.z * light.plane.z) - 1e-3f;
 	}
 	float3 zero = mk3(0.0f, 0.0f, 0.0f);
-	bool single = (t.specular.total <= 0.0f);
+	bool single = (t.specular_total <= 0.0f);
 	if (j == 0 && single) {
 		float r = 1.0f / dd;
 		ray.if_visible = scale3(full, r);

@@ -4,6 +4,7 @@
 // A namespace of its own: the host-side stubs of the shared __device__ functions must not collide with api.cu's.
 #define RL_NS winner_cr
 #define RL_CR_LIBM 1
+#define RL_PSA_ATTR __forceinline__   // the production kernels call the PSA functions once per loop body (shading.cuh)
 #include "internal.h"
 #include "shade_fast.cuh"
 

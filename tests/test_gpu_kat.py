@@ -52,8 +52,14 @@ def test_psa_prepare_and_sample(device, fn, name, P, fast, biased):
         assert np.array_equal(got_poly[:, 35:].view(np.uint32), want_poly[:, 35:].view(np.uint32))
     else:
         total = want_poly[:, 43:44]
-        assert np.all(np.abs(got_poly[:, 35:] - want_poly[:, 35:]) <= 1e-5 * total + 1e-7)
-        same = np.mean(got_poly[:, 35:].view(np.uint32) == want_poly[:, 35:].view(np.uint32))
+        got_a, want_a = got_poly[:, 35:], want_poly[:, 35:]
+        both_nan = np.isnan(got_a) & np.isnan(want_a)     # degenerate polygons (0 / 0 in a tangent) are NaN in the reference, too
+        close = (np.abs(got_a - want_a) <= 1e-5 * np.nan_to_num(total) + 1e-7) | both_nan
+        if not close.all():
+            bad = np.argwhere(~close)[:5]
+            parity_log(f"kat psa {name}: {np.count_nonzero(~close)} sector areas out of tolerance, e.g. " + "; ".join(f"[{i},{j}] got {got_a[i, j]!r} want {want_a[i, j]!r}" for i, j in bad))
+        assert close.all()
+        same = np.mean((got_a.view(np.uint32) == want_a.view(np.uint32)) | both_nan)
         parity_log(f"kat psa {name}: sector areas bit-identical {same:.5f}")
         assert same >= 0.999
     # sampled directions: the iteration amplifies ulps where sectors are thin; 99 % within 1e-4, all unit length and above the horizon

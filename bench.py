@@ -339,12 +339,16 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
     light_bytes = len(app.write_lights())
     triangles = int(wl["scene"]["mesh"]["material_indices"].shape[0])
 
-    # ---- tear down in dependency order before anything else is created: the device object references the gather slab
+    # ---- tear down in dependency order before anything else is created. torch's allocators record an event on every stream
+    # a block was used on when the block is freed, and the stream here belongs to the library's device object: the tensors
+    # (the pinned frame above all) have to go while that stream still exists; only then is the device object destroyed.
     barrier()
+    dev.set_accum_buffer(0)         # the device object must not point into the gather slab any more
+    del gat, flush, host_frame, start, end
     torch.cuda.synchronize()
-    r.close()
-    del gat, flush, host_frame, start, end, stream
     torch.cuda.empty_cache()
+    del stream
+    r.close()
 
     line = None
     if rank == 0:

@@ -128,6 +128,11 @@ int risltc_cuda_render_frames(risltc_device_t* device, const void* per_frame_con
 int risltc_cuda_synchronize(risltc_device_t* device);
 int risltc_cuda_read_accum(risltc_device_t* device, float* rgba);
 int risltc_cuda_read_visibility(risltc_device_t* device, uint32_t* primitive_ids);
+/* The copy pass (copy_pass.frag.glsl:28-58) and the 8-bit swapchain write behind it: the accumulated frame as
+ * owned_rows x width x 3 bytes. frame_bits 0: the displayed image (clamp, linear -> sRGB, srgb_utility.glsl:20-34);
+ * frame_bits 1 / 2: the low / high byte of every channel's half-float bits -- the two LDR frames that
+ * implement_screenshot combines into one HDR screenshot (main.c:2339-2350, 2358-2409). Blocking. */
+int risltc_cuda_copy_pass(risltc_device_t* device, uint32_t frame_bits, uint8_t* rgb8);
 /* Global row index of every owned row (owned_rows entries). */
 int risltc_cuda_owned_row_indices(const risltc_device_t* device, uint32_t* rows);
 

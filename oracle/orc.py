@@ -261,3 +261,11 @@ def world_to_projection(cam, aspect):
     lib().orc_world_to_projection(out, (C.c_float * 3)(*cam["position"]), C.c_float(cam["rotation_x"]), C.c_float(cam["rotation_z"]),
                                   C.c_float(cam["vertical_fov"]), C.c_float(cam["near"]), C.c_float(cam["far"]), C.c_float(aspect))
     return np.array([list(r) for r in out], dtype=np.float32)
+
+
+def copy_pass(rgba, frame_bits=0):
+    """copy_pass.frag.glsl on an (H, W, 4) float32 frame -> (H, W, 3) uint8."""
+    a = np.ascontiguousarray(rgba, dtype=np.float32)
+    out = np.empty(a.shape[:-1] + (3,), dtype=np.uint8)
+    lib().orc_copy_pass(_p(a), C.c_uint64(a.size // 4), C.c_uint32(frame_bits), _p(out))
+    return out

@@ -783,3 +783,45 @@ static v3 decode_normal_32_bit(float ox, float oy) {
 
 /* BVH stand-in, shading-point reconstruction and the three passes (unity build) */
 #include "risltc_oracle_frame.inc"
+
+/* ----------------------------------------------------------------- copy pass */
+
+/* packHalf2x16 for one value: fp32 -> fp16 bits, round to nearest even */
+static uint16_t half_bits_of(float value) {
+	uint32_t x; memcpy(&x, &value, 4);
+	uint32_t sign = (x >> 16) & 0x8000u, mantissa = x & 0x7FFFFFu, biased = (x >> 23) & 0xFFu;
+	int32_t exponent = (int32_t) biased - 127 + 15;
+	if (biased == 0xFFu) return (uint16_t) (sign | 0x7C00u | (mantissa ? 0x200u : 0u));
+	if (exponent >= 31) return (uint16_t) (sign | 0x7C00u);
+	if (exponent <= 0) {
+		if (exponent < -10) return (uint16_t) sign;
+		mantissa |= 0x800000u;
+		uint32_t shift = (uint32_t) (14 - exponent);
+		uint32_t half = mantissa >> shift, rest = mantissa & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+		if (rest > halfway || (rest == halfway && (half & 1u))) ++half;
+		return (uint16_t) (sign | half);
+	}
+	uint32_t half = ((uint32_t) exponent << 10) | (mantissa >> 13), rest = mantissa & 0x1FFFu;
+	if (rest > 0x1000u || (rest == 0x1000u && (half & 1u))) ++half;   /* may carry into the exponent: correct */
+	return (uint16_t) (sign | half);
+}
+
+/* copy_pass.frag.glsl:28-58 + srgb_utility.glsl:20-34 + the UNORM8 write of the swapchain image (round to nearest).
+ * frame_bits 0: display (linear -> sRGB), 1 / 2: low / high byte of the half bits of r, g, b. pow() as glsl_atan above. */
+void orc_copy_pass(const float* rgba, uint64_t pixel_count, uint32_t frame_bits, uint8_t* rgb8) {
+	for (uint64_t i = 0; i != pixel_count; ++i)
+		for (int k = 0; k != 3; ++k) {
+			float v = rgba[4 * i + k];
+			uint32_t byte;
+			if (frame_bits != 0u) {
+				uint32_t h = half_bits_of(v);
+				byte = (frame_bits == 1u) ? (h & 0xFFu) : (h >> 8);
+			}
+			else {
+				float linear = clampf(v, 0.0f, 1.0f);
+				float srgb = (linear <= 0.0031308f) ? (12.92f * linear) : (1.055f * (float) pow((double) linear, (double) (1.0f / 2.4f)) - 0.055f);
+				byte = (uint32_t) (clampf(srgb, 0.0f, 1.0f) * 255.0f + 0.5f);
+			}
+			rgb8[3 * i + k] = (uint8_t) byte;
+		}
+}

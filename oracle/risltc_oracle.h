@@ -162,6 +162,10 @@ uint64_t orc_render_frame(const orc_scene_t* scene, const orc_constants_t* const
 int orc_any_hit(const orc_scene_t* scene, const float origin[3], const float dir[3], float t_min, float t_max);
 int orc_thread_count(void);
 
+/* copy_pass.frag.glsl:28-58 + the 8-bit swapchain write: frame_bits 0 = displayed sRGB image, 1 / 2 = low / high byte of the
+ * half-float bits (the two LDR frames of an HDR screenshot, main.c:2339-2350). rgb8: pixel_count x 3 bytes. */
+void orc_copy_pass(const float* rgba, uint64_t pixel_count, uint32_t frame_bits, uint8_t* rgb8);
+
 #ifdef __cplusplus
 }
 #endif

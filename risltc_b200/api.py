@@ -154,6 +154,12 @@ class Device:
         _check(lib().risltc_cuda_read_visibility(self.h, _p(out)))
         return out
 
+    def copy_pass(self, frame_bits=0):
+        """(owned_rows, width, 3) uint8: the displayed sRGB image (0) or the low (1) / high (2) bytes of the half-float bits."""
+        out = np.empty((self.owned_rows, self.width, 3), dtype=np.uint8)
+        _check(lib().risltc_cuda_copy_pass(self.h, C.c_uint32(frame_bits), _p(out)))
+        return out
+
     def last_frame_ms(self):
         return float(lib().risltc_cuda_last_frame_ms(self.h))
 

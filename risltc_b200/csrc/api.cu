@@ -6,6 +6,7 @@
 #include "trace4.cuh"
 #include "raster.cuh"
 #include "bvh_build.h"
+#include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -595,6 +596,45 @@ extern "C" int risltc_cuda_read_accum(risltc_device_t* d, float* rgba) {
 	if (!rgba || !d->px.accum) return fail("read_accum: nothing to read", nullptr);
 	CU(cudaMemcpyAsync(rgba, d->px.accum, (size_t) d->px.pixel_count * sizeof(float4), cudaMemcpyDeviceToHost, d->stream));
 	CU(cudaStreamSynchronize(d->stream));
+	return 0;
+}
+
+// copy_pass.frag.glsl:28-58 followed by the UNORM8 framebuffer write. frame_bits 0: linear -> sRGB (srgb_utility.glsl:20-34),
+// 1 / 2: the low / high byte of every channel's half-float bits (packHalf2x16 rounds to nearest even)
+__global__ void copy_pass_kernel(const float4* accum, uint8_t* rgb8, uint32_t pixel_count, uint32_t frame_bits) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= pixel_count) return;
+	const float4 c = accum[i];
+	const float channel[3] = { c.x, c.y, c.z };
+	#pragma unroll
+	for (int k = 0; k != 3; ++k) {
+		uint32_t byte;
+		if (frame_bits != 0u) {
+			const uint32_t half_bits = __half_as_ushort(__float2half_rn(channel[k]));
+			byte = (frame_bits == 1u) ? (half_bits & 0xFFu) : (half_bits >> 8);
+		}
+		else {
+			const float linear = fminf(fmaxf(channel[k], 0.0f), 1.0f);
+			// pow() correctly rounded, like the oracle defines GLSL's transcendental functions (common.cuh)
+			const float srgb = (linear <= 0.0031308f) ? (12.92f * linear) : (1.055f * (float) pow((double) linear, (double) (1.0f / 2.4f)) - 0.055f);
+			byte = (uint32_t) (fminf(fmaxf(srgb, 0.0f), 1.0f) * 255.0f + 0.5f);
+		}
+		rgb8[3 * (size_t) i + k] = (uint8_t) byte;
+	}
+}
+
+extern "C" int risltc_cuda_copy_pass(risltc_device_t* d, uint32_t frame_bits, uint8_t* rgb8) {
+	if (use(d)) return 1;
+	if (!rgb8 || !d->px.accum) return fail("copy_pass: nothing to read", nullptr);
+	if (frame_bits > 2u) return fail("copy_pass: frame_bits is 0 (display), 1 (low half bits) or 2 (high half bits)", nullptr);
+	uint8_t* staging = nullptr;
+	const size_t bytes = 3 * (size_t) d->px.pixel_count;
+	CU(cudaMalloc(&staging, bytes));
+	copy_pass_kernel<<<(d->px.pixel_count + 255) / 256, 256, 0, d->stream>>>(d->px.accum, staging, d->px.pixel_count, frame_bits);
+	cudaError_t e = cudaMemcpyAsync(rgb8, staging, bytes, cudaMemcpyDeviceToHost, d->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+	cudaFree(staging);
+	if (e != cudaSuccess) return fail("copy_pass", cudaGetErrorString(e));
 	return 0;
 }
 

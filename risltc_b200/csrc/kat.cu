@@ -41,7 +41,7 @@ __global__ void kat_psa_kernel(const float* polygons, const uint32_t* counts, co
 	for (int k = 0; k != P; ++k) v[k] = mk3(polygons[i * 24 + 3 * k], polygons[i * 24 + 3 * k + 1], polygons[i * 24 + 3 * k + 2]);
 	PsaPolygon<P> p;
 	for (int k = 0; k != P; ++k) { p.v[k] = mk2(0.0f, 0.0f); p.e[k] = mk2(0.0f, 0.0f); p.sector[k] = 0.0f; }
-	psa_prepare<P>(p, counts[i], v, fast != 0);
+	psa_prepare_rt<P>(p, counts[i], v, fast != 0);
 	float* o = out_polygons + (size_t) i * 44;
 	for (int k = 0; k != 44; ++k) o[k] = 0.0f;
 	o[0] = (float) p.vc;
@@ -52,7 +52,7 @@ __global__ void kat_psa_kernel(const float* polygons, const uint32_t* counts, co
 		o[35 + k] = p.sector[k];
 	}
 	o[33] = p.inner0.x; o[34] = p.inner0.y; o[43] = p.total;
-	float3 d = psa_sample<P>(p, randoms[2 * i], randoms[2 * i + 1], fast != 0, biased != 0);
+	float3 d = psa_sample_rt<P>(p, randoms[2 * i], randoms[2 * i + 1], fast != 0, biased != 0);
 	out_dirs[3 * i] = d.x; out_dirs[3 * i + 1] = d.y; out_dirs[3 * i + 2] = d.z;
 }
 

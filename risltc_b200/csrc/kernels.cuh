@@ -66,12 +66,12 @@ __device__ float3 sample_light(ShadeContext<V, DEFER>& c, const ShadingPoint& sp
 	for (uint32_t smp = 0; smp != S; ++smp) {
 		float u0 = c.next(), u1 = c.next();
 		float3 dir[2];
-		dir[0] = psa_sample<V + 1>(t.diffuse, u0, u1, fast, biased);
+		dir[0] = psa_sample_rt<V + 1>(t.diffuse, u0, u1, fast, biased);
 		dir[1] = mk3(0.0f, 0.0f, 0.0f);
 		int techniques = 1;
 		if (t.specular.total > 0.0f) {
 			u0 = c.next(); u1 = c.next();
-			dir[1] = cosine_to_shading_dir(ltc, psa_sample<V + 1>(t.specular, u0, u1, fast, biased));
+			dir[1] = cosine_to_shading_dir(ltc, psa_sample_rt<V + 1>(t.specular, u0, u1, fast, biased));
 			techniques = 2;
 		}
 		for (int j = 0; j != techniques; ++j) {

@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 					PsaPolygon<4> p;
 					#pragma unroll
 					for (int i = 0; i != 4; ++i) { p.v[i] = mk2(0.0f, 0.0f); p.e[i] = mk2(0.0f, 0.0f); p.sector[i] = 0.0f; }
-					psa_prepare<4>(p, vc, pv, false);
+					psa_prepare<4, false>(p, vc, pv);
 					if (tech == 0) { total_d = p.total; live = total_d != 0.0f; }
 					else total_s = p.total;
 					prepared = live && (tech == 0 || total_s > 0.0f);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 				}
 				p.inner0 = mk2(RL_POLY(17), RL_POLY(18)); p.total = RL_POLY(23);
 				const float u0 = noise_next(seed), u1 = noise_next(seed);
-				const float3 d = psa_sample<4>(p, u0, u1, false, false);
+				const float3 d = psa_sample<4, false, false>(p, u0, u1);
 				if (tech == 0) dir0 = d;
 				else dir1 = cosine_to_shading_dir(ltc, d);
 			}

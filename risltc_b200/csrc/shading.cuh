@@ -294,13 +294,20 @@ __device__ __forceinline__ float fast_positive_atan(float y) {   // :84-98
 	rx = fmaf(rx, ry, rz);
 	return (y < 0.0f) ? (RL_PI - rx) : rx;
 }
-__device__ __forceinline__ float positive_atan(float tangent, bool fast) {   // :105-112
-	if (fast) return fast_positive_atan(tangent);
+// USE_FAST_ATAN and the biased sampler are compile-time switches here like in the reference (main.c:962-991). They used to be
+// run-time bools handed down to the out-of-line PSA functions; ptxas 12.9 keeps such a warp-uniform argument in a uniform
+// register, reuses that register for the double-precision atan's constants in one divergent branch (decentral polygons) and
+// reads it afterwards in the other (central polygons of the same warp): whole warps silently took the fast atan. Found by
+// the known-answer test of the PSA preparation once its transcendental functions were correctly rounded.
+template <bool FAST>
+__device__ __forceinline__ float positive_atan(float tangent) {   // :105-112
+	if (FAST) return fast_positive_atan(tangent);
 	return rl_atan(tangent) + ((tangent < 0.0f) ? RL_PI : 0.0f);
 }
-__device__ __forceinline__ float area_from_tangents(float inner_rsqrt, float inner_tan, float outer_rsqrt, float outer_tan, bool fast) {   // :381-386
-	float inner_area = inner_rsqrt * positive_atan(inner_tan, fast);
-	float r = fmaf(outer_rsqrt, positive_atan(outer_tan, fast), -inner_area);
+template <bool FAST>
+__device__ __forceinline__ float area_from_tangents(float inner_rsqrt, float inner_tan, float outer_rsqrt, float outer_tan) {   // :381-386
+	float inner_area = inner_rsqrt * positive_atan<FAST>(inner_tan);
+	float r = fmaf(outer_rsqrt, positive_atan<FAST>(outer_tan), -inner_area);
 	return (r > 0.0f) ? (0.5f * r) : 0.0f;
 }
 __device__ __forceinline__ float mix_fma(float x, float y, float a) { return fmaf(a, y, fmaf(-a, x, x)); }   // :184-186
@@ -337,8 +344,8 @@ __device__ void psa_sort(PsaPolygon<P>& p) {   // :444-506
 }
 
 // prepare_projected_solid_angle_polygon_sampling, :545-613
-template <int P>
-__device__ RL_PSA_ATTR void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
+template <int P, bool FAST>
+__device__ RL_PSA_ATTR void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P]) {
 	p.vc = vc;
 	float2 inner0 = mk2(1.0f, 0.0f);
 	p.v[0] = mk2(v[0].x, v[0].y);
@@ -373,7 +380,7 @@ __device__ RL_PSA_ATTR void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const flo
 			float rs = ellipse_rsqrt_det(p.e[i]);
 			float det_dirs = fmaxf(+0.0f, dot2(d1, rotate_90(d0)));
 			float edot = rs * dot2(d0, ellipse_transform(p.e[i], d1));
-			float area = 0.5f * rs * positive_atan(det_dirs / edot, fast);
+			float area = 0.5f * rs * positive_atan<FAST>(det_dirs / edot);
 			p.sector[i] = (rs > 0.0f) ? area : 0.0f;
 			p.total += p.sector[i];
 		}
@@ -397,7 +404,7 @@ __device__ RL_PSA_ATTR void psa_prepare(PsaPolygon<P>& p, uint32_t vc, const flo
 			float det_dirs = fmaxf(+0.0f, dot2(d1, rotate_90(d0)));
 			float idot = inner_rs * dot2(d0, ellipse_transform(inner, d1));
 			float odot = outer_rs * dot2(d0, ellipse_transform(outer, d1));
-			p.sector[i] = area_from_tangents(inner_rs, det_dirs / idot, outer_rs, det_dirs / odot, fast);
+			p.sector[i] = area_from_tangents<FAST>(inner_rs, det_dirs / idot, outer_rs, det_dirs / odot);
 			p.total += p.sector[i];
 		}
 	}
@@ -411,7 +418,8 @@ __device__ __forceinline__ float2 solve_homogeneous_quadratic(float q00, float q
 }
 
 // sample_sector_between_ellipses, :668-762
-__device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 inner, float2 outer, float2 dir_0, float2 dir_1, bool fast, bool biased) {
+template <bool FAST, bool BIASED>
+__device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 inner, float2 outer, float2 dir_0, float2 dir_1) {
 	float2 q0 = normalize2(dir_0), q2 = normalize2(dir_1);
 	float2 q1 = add2(q0, q2);
 	float i0 = inversesqrt(fmaf(dot2(inner, q0), dot2(inner, q0), 1.0f)), i1 = inversesqrt(ellipse_dir_factor_rsq(inner, q1)), i2 = inversesqrt(fmaf(dot2(inner, q2), dot2(inner, q2), 1.0f));
@@ -430,7 +438,7 @@ __device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 i
 	float2 a = scale2(r2, off1 * o2);
 	float2 b = add2(scale2(r2, off0 * i2), scale2(n0, tq));
 	float2 cur = solve_homogeneous_quadratic(a.x * n0.x - b.x * n1.x, a.y * n0.x - b.y * n1.x, a.x * n0.y - b.x * n1.y, a.y * n0.y - b.y * n1.y);
-	if (!biased) {
+	if (!BIASED) {
 		int iterations = (fabsf(rn.x - 0.5f) <= 0.5f - 1.0e-5f) ? 2 : 0;
 		float inner_rs = ellipse_rsqrt_det(inner), outer_rs = ellipse_rsqrt_det(outer);
 		for (int it = 0; it != iterations; ++it) {
@@ -440,7 +448,7 @@ __device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 i
 			cur = scale2(cur, sc);
 			float2 id = ellipse_transform(inner, cur), od = ellipse_transform(outer, cur);
 			float det_dirs = fmaxf(+0.0f, dot2(cur, rotate_90(q0)));
-			float err = target_area - area_from_tangents(inner_rs, det_dirs / (inner_rs * dot2(q0, id)), outer_rs, det_dirs / (outer_rs * dot2(q0, od)), fast);
+			float err = target_area - area_from_tangents<FAST>(inner_rs, det_dirs / (inner_rs * dot2(q0, id)), outer_rs, det_dirs / (outer_rs * dot2(q0, od)));
 			float2 c = sub2(id, od), rc = rotate_90(cur), e2 = scale2(id, 2.0f * err);
 			cur = solve_homogeneous_quadratic(c.x * rc.x - e2.x * od.x, c.y * rc.x - e2.y * od.x, c.x * rc.y - e2.x * od.y, c.y * rc.y - e2.y * od.y);
 		}
@@ -451,8 +459,8 @@ __device__ float2 sample_between_ellipses(float2 rn, float target_area, float2 i
 }
 
 // sample_projected_solid_angle_polygon, :772-828
-template <int P>
-__device__ RL_PSA_ATTR float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
+template <int P, bool FAST, bool BIASED>
+__device__ RL_PSA_ATTR float3 psa_sample(const PsaPolygon<P>& p, float u0, float u1) {
 	float target = u0 * p.total;
 	float2 s, outer = mk2(0.0f, 0.0f), d0 = mk2(0.0f, 0.0f);
 	if (p.inner0.x > 0.0f) {
@@ -484,9 +492,20 @@ __device__ RL_PSA_ATTR float3 psa_sample(const PsaPolygon<P>& p, float u0, float
 			d0 = p.v[i]; d1 = p.v[i + 1]; sector_psa = p.sector[i];
 			if ((i >= 1 && (uint32_t) i + 2u == p.vc) || target < sector_psa) break;
 		}
-		s = sample_between_ellipses(mk2(target / sector_psa, u1), target, inner, outer, d0, d1, fast, biased);
+		s = sample_between_ellipses<FAST, BIASED>(mk2(target / sector_psa, u1), target, inner, outer, d0, d1);
 	}
 	return mk3(s.x, s.y, sqrtf(fmaxf(0.0f, fmaf(-s.x, s.x, fmaf(-s.y, s.y, 1.0f)))));
+}
+
+// run-time selection between the compiled variants, at the call site (the flags come straight from kernel parameters there)
+template <int P>
+__device__ __forceinline__ void psa_prepare_rt(PsaPolygon<P>& p, uint32_t vc, const float3 (&v)[P], bool fast) {
+	if (fast) psa_prepare<P, true>(p, vc, v); else psa_prepare<P, false>(p, vc, v);
+}
+template <int P>
+__device__ __forceinline__ float3 psa_sample_rt(const PsaPolygon<P>& p, float u0, float u1, bool fast, bool biased) {
+	if (fast) return biased ? psa_sample<P, true, true>(p, u0, u1) : psa_sample<P, true, false>(p, u0, u1);
+	return biased ? psa_sample<P, false, true>(p, u0, u1) : psa_sample<P, false, false>(p, u0, u1);
 }
 
 // ------------------------------------------------------------------- BRDF
@@ -625,11 +644,11 @@ __device__ void prepare_techniques(Techniques<V>& t, const ShadingPoint& sp, con
 	pv[V] = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t vc = clip_to_horizon<V + 1>(light.count, pv, var.min_light_vertices);
 	if (vc == 0) return;
-	psa_prepare<V + 1>(t.diffuse, vc, pv, fast);
+	psa_prepare_rt<V + 1>(t.diffuse, vc, pv, fast);
 	#pragma unroll
 	for (int i = 0; i != V; ++i) pv[i] = to_cosine_space(ltc, light.v[i], t.flip);
 	vc = clip_to_horizon<V + 1>(light.count, pv, var.min_light_vertices);
-	if (vc != 0) psa_prepare<V + 1>(t.specular, vc, pv, fast);
+	if (vc != 0) psa_prepare_rt<V + 1>(t.specular, vc, pv, fast);
 	if (t.diffuse.total == 0.0f) return;
 	technique_weights(t, sp, ltc.albedo, t.diffuse.total, t.specular.total, light.radiance, var.mis_heuristic == MIS_OPTIMAL);
 	t.valid = true;

@@ -172,3 +172,18 @@ def read_ltc_fits(directory, fresnel_count):
         (res,) = struct.unpack_from("<Q", data, 0)
         out.append(np.frombuffer(data, "<f4", res * res * 5, 8).reshape(res, res, 5))
     return np.stack(out)
+
+
+# --------------------------------------------------------------------- .hdr
+def read_hdr(path):
+    """Radiance RGBE with flat (non run-length) scanlines, as write_hdr_screenshot (host/application.c) and stb_image_write's
+    stbi_write_hdr for narrow images store them; returns (H, W, 3) float32."""
+    data = Path(path).read_bytes()
+    end = data.index(b"\n\n") + 2
+    line_end = data.index(b"\n", end)
+    parts = data[end:line_end].split()
+    assert parts[0] == b"-Y" and parts[2] == b"+X", parts
+    H, W = int(parts[1]), int(parts[3])
+    rgbe = np.frombuffer(data, np.uint8, H * W * 4, line_end + 1).reshape(H, W, 4)
+    scale = np.where(rgbe[..., 3:4] == 0, 0.0, np.ldexp(1.0, rgbe[..., 3:4].astype(np.int32) - 136))
+    return (rgbe[..., :3].astype(np.float64) * scale).astype(np.float32)

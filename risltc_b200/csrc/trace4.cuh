@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 				if (mine < stage_count) {
 					const float4 a0 = stage[mine][0], a1 = stage[mine][1];
 					ray = __float_as_uint(a1.w); busy = true;
+					if (COUNT) ++n_rays;
 					o = mk3(a0.x, a0.y, a0.z); d = mk3(a1.x, a1.y, a1.z); t_max = a0.w;
 					// box tests only: the error of the approximate reciprocal is covered by the outward rounding of the boxes
 					inv = mk3(box_reciprocal(d.x), box_reciprocal(d.y), box_reciprocal(d.z));

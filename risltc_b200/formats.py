@@ -174,16 +174,65 @@ def read_ltc_fits(directory, fresnel_count):
     return np.stack(out)
 
 
-# --------------------------------------------------------------------- .hdr
+# --------------------------------------------------------------------- .hdr / .png
 def read_hdr(path):
-    """Radiance RGBE with flat (non run-length) scanlines, as write_hdr_screenshot (host/application.c) and stb_image_write's
-    stbi_write_hdr for narrow images store them; returns (H, W, 3) float32."""
+    """Radiance RGBE, flat or adaptive run-length scanlines (what host/screenshot.c and stb_image_write store);
+    returns (H, W, 3) float32."""
     data = Path(path).read_bytes()
     end = data.index(b"\n\n") + 2
     line_end = data.index(b"\n", end)
     parts = data[end:line_end].split()
     assert parts[0] == b"-Y" and parts[2] == b"+X", parts
     H, W = int(parts[1]), int(parts[3])
-    rgbe = np.frombuffer(data, np.uint8, H * W * 4, line_end + 1).reshape(H, W, 4)
+    raw = np.frombuffer(data, np.uint8, offset=line_end + 1)
+    rgbe = np.zeros((H, W, 4), dtype=np.uint8)
+    pos = 0
+    for y in range(H):
+        if W < 8 or W >= 32768 or not (raw[pos] == 2 and raw[pos + 1] == 2 and (int(raw[pos + 2]) << 8 | int(raw[pos + 3])) == W):
+            rgbe[y] = raw[pos:pos + 4 * W].reshape(W, 4); pos += 4 * W
+            continue
+        pos += 4
+        for c in range(4):
+            x = 0
+            while x < W:
+                n = int(raw[pos]); pos += 1
+                if n > 128:
+                    rgbe[y, x:x + n - 128, c] = raw[pos]; pos += 1; x += n - 128
+                else:
+                    rgbe[y, x:x + n, c] = raw[pos:pos + n]; pos += n; x += n
+            assert x == W
     scale = np.where(rgbe[..., 3:4] == 0, 0.0, np.ldexp(1.0, rgbe[..., 3:4].astype(np.int32) - 136))
     return (rgbe[..., :3].astype(np.float64) * scale).astype(np.float32)
+
+
+def read_png(path):
+    """8-bit truecolour PNG without interlacing (what host/screenshot.c stores); returns (H, W, 3) uint8. Checks every CRC."""
+    import zlib
+    data = Path(path).read_bytes()
+    assert data[:8] == bytes([137, 80, 78, 71, 13, 10, 26, 10])
+    pos, idat, W, H = 8, b"", 0, 0
+    while pos < len(data):
+        (length,) = struct.unpack_from(">I", data, pos)
+        kind, body = data[pos + 4:pos + 8], data[pos + 8:pos + 8 + length]
+        (crc,) = struct.unpack_from(">I", data, pos + 8 + length)
+        assert zlib.crc32(kind + body) == crc, kind
+        if kind == b"IHDR":
+            W, H, depth, colour, compression, flt, interlace = struct.unpack(">IIBBBBB", body)
+            assert (depth, colour, compression, flt, interlace) == (8, 2, 0, 0, 0)
+        elif kind == b"IDAT":
+            idat += body
+        pos += 12 + length
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(H, 3 * W + 1)
+    out = np.zeros((H, 3 * W), dtype=np.uint8)
+    for y in range(H):   # undo the scanline filters (types 0-2 suffice for files written here and by simple encoders)
+        f, line = int(raw[y, 0]), raw[y, 1:].astype(np.int32)
+        if f == 0:
+            out[y] = line
+        elif f == 1:
+            for x in range(3 * W):
+                out[y, x] = (line[x] + (int(out[y, x - 3]) if x >= 3 else 0)) & 255
+        elif f == 2:
+            out[y] = (line + (out[y - 1].astype(np.int32) if y else 0)) & 255
+        else:
+            raise ValueError(f"PNG filter {f} not supported")
+    return out.reshape(H, W, 3)

@@ -105,6 +105,11 @@ class Application:
         if lib().risltc_app_render_frames(self.h, C.c_uint32(count), C.c_int(int(upload_lights))):
             raise RuntimeError("risltc_app_render_frames failed")
 
+    def screenshot(self, png=None, hdr=None):
+        """implement_screenshot (main.c:2358-2409) of the accumulated frame: 8-bit sRGB *.png and / or RGBE *.hdr."""
+        if lib().risltc_app_screenshot(self.h, str(png).encode() if png else None, str(hdr).encode() if hdr else None):
+            raise RuntimeError("taking the screenshot failed (see the message printed above)")
+
     def wait_ms(self):
         return float(lib().risltc_app_wait(self.h))
 

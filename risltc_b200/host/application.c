@@ -1,7 +1,7 @@
 /* application.c -- the offline frame path of the reference's main.c on top of the C ABI:
  * quicksaves (main.c:45-125), defaults (:129-236), per-frame constants (:2902-2946), the light
  * buffer (:456-490), start-up / update / one frame (:2569, :2467, :2955), the experiment state
- * machine (:2647-2790) and *.hdr screenshots (:2339-2409). No window, no swapchain, no GUI. */
+ * machine (:2647-2790); screenshots (:2339-2409) are in screenshot.c. No window, no swapchain, no GUI. */
 #include "risltc_host.h"
 #include "risltc_cuda.h"
 #include <math.h>
@@ -378,70 +378,6 @@ int read_accumulation_buffer(application_t* app, float* rgba) {
 
 /* --------------------------------------------------------------- screenshots */
 
-static uint16_t float_to_half_bits(float value) {   /* packHalf2x16: round to nearest even */
-	uint32_t x; memcpy(&x, &value, 4);
-	uint32_t sign = (x >> 16) & 0x8000u, mantissa = x & 0x7FFFFFu;
-	int32_t exponent = (int32_t) ((x >> 23) & 0xFFu) - 127 + 15;
-	if (((x >> 23) & 0xFFu) == 0xFFu) return (uint16_t) (sign | 0x7C00u | (mantissa ? 0x200u : 0u));
-	if (exponent >= 31) return (uint16_t) (sign | 0x7C00u);
-	if (exponent <= 0) {
-		if (exponent < -10) return (uint16_t) sign;
-		mantissa |= 0x800000u;
-		uint32_t shift = (uint32_t) (14 - exponent);
-		uint32_t half = mantissa >> shift, rest = mantissa & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
-		if (rest > halfway || (rest == halfway && (half & 1u))) ++half;
-		return (uint16_t) (sign | half);
-	}
-	uint32_t half = ((uint32_t) exponent << 10) | (mantissa >> 13), rest = mantissa & 0x1FFFu;
-	if (rest > 0x1000u || (rest == 0x1000u && (half & 1u))) ++half;
-	return (uint16_t) (sign | half);
-}
-
-static float half_bits_to_float(uint16_t h) {
-	uint32_t sign = ((uint32_t) h & 0x8000u) << 16, exponent = (h >> 10) & 0x1Fu, mantissa = h & 0x3FFu, x;
-	if (exponent == 0) {
-		if (mantissa == 0) x = sign;
-		else {
-			int e = -1;
-			do { ++e; mantissa <<= 1; } while (!(mantissa & 0x400u));
-			x = sign | ((uint32_t) (127 - 15 - e) << 23) | ((mantissa & 0x3FFu) << 13);
-		}
-	}
-	else if (exponent == 31) x = sign | 0x7F800000u | (mantissa << 13);
-	else x = sign | ((exponent + 127 - 15) << 23) | (mantissa << 13);
-	float f; memcpy(&f, &x, 4);
-	return f;
-}
-
-/* Radiance RGBE, flat (non run-length) scanlines; the pixel values pass through fp16 first, like
- * the reference's two-LDR-frame capture of half bits does (copy_pass.frag.glsl:37-53, main.c:2339-2350). */
-int write_hdr_screenshot(const char* path, const float* rgba, uint32_t width, uint32_t height) {
-	FILE* file = fopen(path, "wb");
-	if (!file) {
-		printf("Failed to store a screenshot to the *.hdr file at %s. Please check path and permissions.\n", path);
-		return 1;
-	}
-	fprintf(file, "#?RADIANCE\n# Written by risltc-b200\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y %u +X %u\n", height, width);
-	for (size_t i = 0; i != (size_t) width * height; ++i) {
-		float rgb[3];
-		for (int c = 0; c != 3; ++c) rgb[c] = half_bits_to_float(float_to_half_bits(rgba[4 * i + c]));
-		float largest = fmaxf(rgb[0], fmaxf(rgb[1], rgb[2]));
-		unsigned char rgbe[4] = { 0, 0, 0, 0 };
-		if (largest >= 1e-32f) {
-			int exponent;
-			float normalize = frexpf(largest, &exponent) * 256.0f / largest;
-			rgbe[0] = (unsigned char) (rgb[0] * normalize);
-			rgbe[1] = (unsigned char) (rgb[1] * normalize);
-			rgbe[2] = (unsigned char) (rgb[2] * normalize);
-			rgbe[3] = (unsigned char) (exponent + 128);
-		}
-		fwrite(rgbe, 1, 4, file);
-	}
-	fclose(file);
-	printf("Wrote screenshot to %s.\n", path);
-	return 0;
-}
-
 static int take_experiment_screenshot(application_t* app, uint32_t index) {
 	const experiment_t* e = app->experiment_list.experiment;
 	if (!e) return 0;
@@ -452,10 +388,9 @@ static int take_experiment_screenshot(application_t* app, uint32_t index) {
 	char* relative = (char*) malloc(n);
 	snprintf(relative, n, "%s%s%s.%s", e->base_dir, e->exp_name, name, e->ext);
 	char* path = resolve_path(relative);
-	size_t pixels = (size_t) app->swapchain.extent.width * app->swapchain.extent.height;
-	float* rgba = (float*) malloc(pixels * 4 * sizeof(float));
-	int result = read_accumulation_buffer(app, rgba) || write_hdr_screenshot(path, rgba, app->swapchain.extent.width, app->swapchain.extent.height);
-	free(rgba); free(path); free(relative);
+	/* experiment_t.use_hdr: *.hdr through the two half-bit frames, else *.png (main.c:2757-2760) */
+	int result = e->use_hdr ? take_screenshot(app, NULL, path) : take_screenshot(app, path, NULL);
+	free(path); free(relative);
 	return result;
 }
 

@@ -81,3 +81,8 @@ float risltc_app_wait(application_t* app) {
 	app->last_frame_ms = risltc_cuda_last_frame_ms(app->device.cuda);
 	return app->last_frame_ms;
 }
+
+/* implement_screenshot of the frame in the accumulation buffer (screenshot.c); NULL skips a format */
+int risltc_app_screenshot(application_t* app, const char* path_png, const char* path_hdr) {
+	return take_screenshot(app, path_png, path_hdr);
+}

@@ -381,7 +381,15 @@ EXTERN_C int advance_experiments(application_t* app);
 EXTERN_C void destroy_application(application_t* app);
 /* The accumulated frame as RGBA32F (rows owned by this process, see stripe_*). */
 EXTERN_C int read_accumulation_buffer(application_t* app, float* rgba);
-/* implement_screenshot for *.hdr (main.c:2358-2409): values go through fp16 like the copy pass does */
+/* implement_screenshot (main.c:2358-2409, screenshot.c): the accumulated frame through the copy pass to *.png (8-bit sRGB) and /
+ * or *.hdr (two frames of half-float bits combined, Radiance RGBE); either path may be NULL */
+EXTERN_C int take_screenshot(application_t* app, const char* path_png, const char* path_hdr);
+EXTERN_C void combine_ldr_screenshots_into_hdr(float* hdr, const uint8_t* low_bits, const uint8_t* high_bits, size_t entry_count);
+EXTERN_C float half_to_float(uint16_t half_bits);
+EXTERN_C uint16_t float_to_half(float value);
+EXTERN_C int write_png(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height);
+EXTERN_C int write_hdr(const char* path, const float* rgb, uint32_t width, uint32_t height);
+/* an RGBA32F frame to *.hdr; the values go through fp16 like the copy pass's two half-bit frames do */
 EXTERN_C int write_hdr_screenshot(const char* path, const float* rgba, uint32_t width, uint32_t height);
 /* -run_exp / -e<N> command line of the reference's main() (main.c:3044-3078) */
 EXTERN_C int risltc_main(int argc, char** argv);

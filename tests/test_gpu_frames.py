@@ -307,3 +307,39 @@ def test_host_layer_path_equals_direct_path(ltc_tables, tmp_path):
 def C_string(c):
     import ctypes
     return ctypes.string_at(ctypes.byref(c), 256)
+
+
+def test_output_stage(ltc_tables, tmp_path):
+    """The copy pass (copy_pass.frag.glsl:28-58, srgb_utility.glsl:20-34) and implement_screenshot (main.c:2339-2409): the
+    8-bit frames of the device equal the oracle's on the same accumulation buffer, the *.png decodes to the displayed
+    frame and the *.hdr to the fp16 image assembled from the two half-bit frames."""
+    from oracle import orc
+    from risltc_b200 import formats, host, scenes
+    fits, rgba, rg = ltc_tables
+    W, H = 200, 120
+    scene = scenes.many_light_room(16, 20, seed=12, width=W, height=H)
+    idx = np.minimum(np.arange(51) * rgba.shape[0] // 51, rgba.shape[0] - 1)
+    vks, tex, save = host.write_scene_files(scene, tmp_path, ltc_fits=np.asarray(fits)[idx])
+    app = host.Application(tmp_path)
+    try:
+        app.load(vks, tex, save, W, H)
+        app.settings(accum=1)
+        app.reset(0)
+        app.render_frames(3)
+        dev = app.device()
+        accum = dev.read_accum()
+        frames = [dev.copy_pass(k) for k in range(3)]
+        app.screenshot(png=tmp_path / "shot.png", hdr=tmp_path / "shot.hdr")
+    finally:
+        app.close()
+    for k in (1, 2):
+        assert np.array_equal(frames[k], orc.copy_pass(accum, k)), f"half-bit frame {k}"
+    display = orc.copy_pass(accum, 0)
+    off = np.abs(frames[0].astype(int) - display.astype(int))
+    parity_log(f"copy pass {W}x{H}: displayed frame differs from the oracle in {np.count_nonzero(off)} of {off.size} bytes (max {off.max()})")
+    assert off.max() <= 1 and np.count_nonzero(off) <= 3      # pow() is correctly rounded on both sides
+    assert np.array_equal(formats.read_png(tmp_path / "shot.png"), frames[0])
+    want = accum[..., :3].astype(np.float16).astype(np.float32)
+    got = formats.read_hdr(tmp_path / "shot.hdr")
+    assert np.all(np.abs(got - want) <= want.max(axis=-1, keepdims=True) * 2.0 ** -7 + 1e-30)
+    assert (frames[0].max() == 255) and (frames[0].min() == 0)

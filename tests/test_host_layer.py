@@ -162,6 +162,39 @@ def test_hdr_writer(lib, tmp_path):
     assert np.allclose([px[0] * 2.0 ** e, px[1] * 2.0 ** e, px[2] * 2.0 ** e], [0.5, 2.0, 0.125], rtol=0.02)
 
 
+def test_screenshot_encoders_round_trip(lib, tmp_path):
+    """screenshot.c: PNG (stored deflate, CRCs, Adler-32) and run-length Radiance files decode to what was stored; the two
+    half-bit frames combine to the fp16 image (main.c:2339-2350); the oracle's copy pass supplies the frames."""
+    from oracle import orc
+    from risltc_b200 import formats
+    rng = np.random.default_rng(5)
+    H, W = 37, 301
+    rgba = (rng.random((H, W, 4)) * np.exp(rng.uniform(-9, 4, (H, W, 1)))).astype(np.float32)
+    rgba[5:9, 10:200] = rgba[5, 10]          # long runs
+    rgba[20, :, :3] = 0.0
+    display, low, high = orc.copy_pass(rgba, 0), orc.copy_pass(rgba, 1), orc.copy_pass(rgba, 2)
+    png = tmp_path / "shot.png"
+    assert lib.write_png(str(png).encode(), display.ctypes.data_as(C.c_void_p), C.c_uint32(W), C.c_uint32(H)) == 0
+    assert np.array_equal(formats.read_png(png), display)
+    hdr = np.zeros((H, W, 3), dtype=np.float32)
+    lib.combine_ldr_screenshots_into_hdr(hdr.ctypes.data_as(C.c_void_p), low.ctypes.data_as(C.c_void_p), high.ctypes.data_as(C.c_void_p), C.c_size_t(hdr.size))
+    want = rgba[..., :3].astype(np.float16).astype(np.float32)
+    assert np.array_equal(hdr.view(np.uint32), want.view(np.uint32))
+    path = tmp_path / "shot.hdr"
+    assert lib.write_hdr(str(path).encode(), hdr.ctypes.data_as(C.c_void_p), C.c_uint32(W), C.c_uint32(H)) == 0
+    got = formats.read_hdr(path)
+    tolerance = want.max(axis=-1, keepdims=True) * 2.0 ** -7 + 1e-30
+    assert np.all(np.abs(got - want) <= tolerance)
+    assert path.stat().st_size < 4 * W * H      # the runs were found
+    # narrow images are stored flat, like stb does
+    assert lib.write_hdr(str(path).encode(), hdr[:, :5].copy().ctypes.data_as(C.c_void_p), C.c_uint32(5), C.c_uint32(H)) == 0
+    assert np.all(np.abs(formats.read_hdr(path) - want[:, :5]) <= tolerance[:, :5])
+    # srgb_utility.glsl:20-34 against a float64 evaluation of the same curve
+    lin = np.clip(rgba[..., :3].astype(np.float64), 0.0, 1.0)
+    srgb = np.where(lin <= 0.0031308, 12.92 * lin, 1.055 * lin ** (1.0 / 2.4) - 0.055)
+    assert np.abs(display.astype(int) - np.floor(srgb * 255.0 + 0.5).astype(int)).max() <= 1
+
+
 @pytest.mark.parametrize("max_leaf", [1, 2, 4])
 def test_acceleration_structures_hold_their_invariants(max_leaf):
     """Host-only: the binary BVH and its 4-wide collapse with 8-bit boxes (risltc_b200/csrc/bvh_build.cpp) for a generated

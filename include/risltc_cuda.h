@@ -52,8 +52,22 @@ int risltc_cuda_upload_scene(risltc_device_t* device, const uint32_t* quantized_
 
 /* Material textures (scene.c:520-552, sampled at shading_pass.frag.glsl:629-633). One record of
  * 8 floats per material: base colour rgb (linear), specular texel rgb (occlusion, linear
- * roughness, metalicity), normal-map texel rg. Flat-colour materials only in this round. */
+ * roughness, metalicity), normal-map texel rg: materials without texture detail (1 x 1 textures); the kernels then skip
+ * the texture-coordinate derivatives and the three filtered fetches. Replaces the textures of upload_textures. */
 int risltc_cuda_upload_materials(risltc_device_t* device, const float* material_constants, uint64_t material_count);
+
+/* Material textures with their mip chains (load_2d_textures, textures.c:95-241; sampler scene.c:546-552): 3 per material in the
+ * order base colour, specular, normal (scene.h:104-118). Every level is decoded to RGBA texels (the host layer decodes the
+ * BC1 / BC5 blocks of *.vkt files), largest level first, tightly packed. Sampled like textureGrad under the stated
+ * definition of DESIGN.md (isotropic level of detail, trilinear, repeat). Replaces the constants of upload_materials. */
+#define RISLTC_TEXEL_RGBA32F 0u
+#define RISLTC_TEXEL_RGBA8_UNORM 1u
+#define RISLTC_TEXEL_RGBA8_SRGB 2u      /* r, g, b through the sRGB curve, alpha linear */
+typedef struct risltc_texture_s {
+	uint32_t format, width, height, mip_count;
+	const void* texels;
+} risltc_texture_t;
+int risltc_cuda_upload_textures(risltc_device_t* device, const risltc_texture_t* textures, uint64_t texture_count);
 
 /* Light buffer: the byte stream write_lights produces (main.c:456-490): per light 12 floats
  * {radiance.xyz, pad, plane.xyzw, vertex_count(u32), pad x3} + max_vertex_count x {x, y, z, pad}. */
@@ -82,7 +96,9 @@ int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
  *   visibility pass (visibility_pass.*.glsl): the triangle-parallel rasteriser or the per-pixel BVH walk; AUTO (default)
  *     times both on the first two frames after upload_scene / resize and keeps the faster;
  *   ray queries (shading_pass.frag.glsl:112-129): the 4-wide tree with 8-bit boxes (default) or the binary tree.
- * This call pins them (the environment variables RISLTC_GBUFFER=raster|bvh and RISLTC_TRACE=4|2 do the same at create). */
+ * This call pins them (the environment variables RISLTC_GBUFFER=raster|bvh and RISLTC_TRACE=4|2 do the same at create).
+ * The shadow-ray kernel additionally times two settings of its triangle-track threshold on the first two frames after
+ * upload_scene and keeps the faster (RISLTC_TRI_VOTE=<n> pins it); results do not depend on it either. */
 #define RISLTC_GBUFFER_BVH 0u
 #define RISLTC_GBUFFER_RASTER 1u
 #define RISLTC_GBUFFER_AUTO 2u

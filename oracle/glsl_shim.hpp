@@ -247,7 +247,11 @@ inline vec4 operator*(const mat4& m, vec4 v) {
 struct utextureBuffer { const void* data; int bytes_per_texel; };
 struct textureBuffer { const uint16_t* data; };
 struct usubpassInput { uint value; };
-struct sampler2D { float texel[4]; };
+// a material texture: either flat (texel) or a texture object of the caller that the caller's sampler reads (the oracle's
+// definition of textureGrad, orc_sample_texture_grad: texture filtering is driver code, not in the tree)
+typedef void (*sample_texture_fn)(const void* texture, const float* uv, const float* ddx, const float* ddy, float* rgba);
+extern sample_texture_fn g_sample_texture;
+struct sampler2D { float texel[4]; const void* texture; };
 struct sampler2DArray { const uint16_t* data; int channels, res, layers; };
 struct accelerationStructureEXT { int unused; };
 struct rayQueryEXT { bool hit; vec3 origin, direction; float t_min, t_max; };
@@ -261,7 +265,12 @@ inline vec4 texelFetch(const textureBuffer& b, int i) {
 	return vec4((float) p[0] / 65535.0f, (float) p[1] / 65535.0f, (float) p[2] / 65535.0f, (float) p[3] / 65535.0f);
 }
 inline uvec4 subpassLoad(const usubpassInput& s) { return uvec4(s.value, 0, 0, 0); }
-inline vec4 textureGrad(const sampler2D& s, vec2, vec2, vec2) { return vec4(s.texel[0], s.texel[1], s.texel[2], s.texel[3]); }
+inline vec4 textureGrad(const sampler2D& s, vec2 uv, vec2 ddx, vec2 ddy) {
+	if (!s.texture) return vec4(s.texel[0], s.texel[1], s.texel[2], s.texel[3]);
+	float c[2] = { uv.x, uv.y }, dx[2] = { ddx.x, ddx.y }, dy[2] = { ddy.x, ddy.y }, out[4];
+	g_sample_texture(s.texture, c, dx, dy, out);
+	return vec4(out[0], out[1], out[2], out[3]);
+}
 inline vec4 textureLod(const sampler2DArray& s, vec3 coord, float) {
 	int res = s.res;
 	int layer = (int) std::floor(coord.z + 0.5f);

@@ -46,7 +46,37 @@ class Scene(C.Structure):
                 ("positions", C.c_void_p), ("normals_uv", C.c_void_p), ("material_indices", C.c_void_p),
                 ("material_count", C.c_uint64), ("materials", C.c_void_p), ("light_count", C.c_uint32),
                 ("light_records", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
-                ("ltc_rgba16", C.c_void_p), ("ltc_rg16", C.c_void_p), ("bvh", C.c_void_p)]
+                ("ltc_rgba16", C.c_void_p), ("ltc_rg16", C.c_void_p), ("bvh", C.c_void_p), ("textures", C.c_void_p)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("format", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("mip_count", C.c_uint32), ("texels", C.c_void_p)]
+
+
+TEXEL = dict(rgba32f=0, rgba8_unorm=1, rgba8_srgb=2)
+
+
+def pack_textures(textures):
+    """textures: list of dicts {format: 'rgba32f' | 'rgba8_unorm' | 'rgba8_srgb', levels: [(h, w, 4) arrays, largest first]}.
+    Returns (ctypes array of Texture, list of the packed numpy buffers that must stay alive)."""
+    arr = (Texture * len(textures))()
+    keep = []
+    for i, t in enumerate(textures):
+        dtype = np.float32 if t["format"] == "rgba32f" else np.uint8
+        buf = np.concatenate([np.ascontiguousarray(l, dtype=dtype).reshape(-1) for l in t["levels"]])
+        keep.append(buf)
+        arr[i].format = TEXEL[t["format"]]
+        arr[i].height, arr[i].width = t["levels"][0].shape[:2]
+        arr[i].mip_count = len(t["levels"])
+        arr[i].texels = buf.ctypes.data
+    return arr, keep
+
+
+def sample_texture_grad(texture, uv, ddx, ddy):
+    arr, keep = pack_textures([texture])
+    out = (C.c_float * 4)()
+    lib().orc_sample_texture_grad(C.byref(arr[0]), (C.c_float * 2)(*uv), (C.c_float * 2)(*ddx), (C.c_float * 2)(*ddy), out)
+    return np.array(list(out), dtype=np.float32)
 
 
 class PsaPolygon(C.Structure):
@@ -73,6 +103,7 @@ def lib():
         _lib.orc_wang_random_number.restype = C.c_uint32
         _lib.orc_noise_seed.restype = C.c_uint32
         _lib.orc_clip_polygon.restype = C.c_uint32
+        _lib.orc_srgb8_to_linear.restype = C.c_float
     return _lib
 
 
@@ -167,6 +198,14 @@ class OracleScene:
         s.light_count, s.light_records = self.records.shape[0], _p(self.records)
         s.ltc_layers, s.ltc_res = self.rgba16.shape[0], self.rgba16.shape[1]
         s.ltc_rgba16, s.ltc_rg16 = _p(self.rgba16), _p(self.rg16)
+        # material textures (3 per material) when the scene has them; flat materials otherwise
+        self.textures = None
+        tex = arrays.get("textures") if isinstance(arrays, dict) else None
+        if tex is None and scene is not None:
+            tex = scene.get("textures")
+        if tex is not None:
+            self.textures, self._texture_buffers = pack_textures(tex)
+            s.textures = C.cast(self.textures, C.c_void_p)
         self.c = s
         lib().orc_build_bvh(C.byref(s))
 

@@ -51,6 +51,11 @@ class RefShading:
                                 _p(oscene.records), C.c_uint32(oscene.records.shape[0]), C.c_uint32(oscene.records.shape[1]),
                                 _p(oscene.rgba16), _p(oscene.rg16), C.c_uint32(oscene.rgba16.shape[1]), C.c_uint32(oscene.rgba16.shape[0]),
                                 any_hit, C.byref(oscene.c))
+        if oscene.textures is not None:
+            self.lib.ref_bind_textures(C.cast(oscene.textures, C.c_void_p), C.c_uint32(C.sizeof(orc.Texture)), C.c_uint32(len(oscene.textures)),
+                                       C.cast(orc.lib().orc_sample_texture_grad, C.c_void_p))
+        else:
+            self.lib.ref_bind_textures(None, C.c_uint32(0), C.c_uint32(0), None)
 
     def render(self, constants_list, accum=None, accum_start=0):
         """Visibility from the oracle (driver stand-in), shading by the compiled reference, accumulation

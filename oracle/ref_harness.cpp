@@ -18,6 +18,7 @@
 
 namespace glsl {
 any_hit_fn g_any_hit = nullptr;
+sample_texture_fn g_sample_texture = nullptr;
 const void* g_any_hit_scene = nullptr;
 thread_local unsigned long long g_ray_count = 0;
 int g_rt_light_count = 1;
@@ -43,7 +44,7 @@ void ref_bind_scene(const uint32_t* positions, const uint16_t* normals_uv, const
 	g_material_indices.data = material_indices; g_material_indices.bytes_per_texel = 1;
 	for (uint32_t i = 0; i != material_count && i != MATERIAL_COUNT; ++i) {
 		const float* m = material_constants + 8 * i;
-		sampler2D base = { { m[0], m[1], m[2], 1.0f } }, spec = { { m[3], m[4], m[5], 1.0f } }, nrm = { { m[6], m[7], 1.0f, 1.0f } };
+		sampler2D base = { { m[0], m[1], m[2], 1.0f }, nullptr }, spec = { { m[3], m[4], m[5], 1.0f }, nullptr }, nrm = { { m[6], m[7], 1.0f, 1.0f }, nullptr };
 		g_material_textures[3 * i + 0] = base; g_material_textures[3 * i + 1] = spec; g_material_textures[3 * i + 2] = nrm;
 	}
 	g_rt_light_count = (int) light_count;
@@ -60,6 +61,14 @@ void ref_bind_scene(const uint32_t* positions, const uint16_t* normals_uv, const
 	g_ltc_tables[0].data = ltc_rgba16; g_ltc_tables[0].channels = 4; g_ltc_tables[0].res = (int) ltc_res; g_ltc_tables[0].layers = (int) ltc_layers;
 	g_ltc_tables[1].data = ltc_rg16; g_ltc_tables[1].channels = 2; g_ltc_tables[1].res = (int) ltc_res; g_ltc_tables[1].layers = (int) ltc_layers;
 	g_any_hit = any_hit; g_any_hit_scene = any_hit_scene;
+}
+
+// Material textures (binding 5) as texture objects of the caller, 3 per material, sampled through the caller's textureGrad
+// (null: back to the flat texels of ref_bind_scene)
+void ref_bind_textures(const void* textures, uint32_t stride_bytes, uint32_t texture_count, sample_texture_fn sample) {
+	g_sample_texture = sample;
+	for (uint32_t i = 0; i != 3 * MATERIAL_COUNT; ++i)
+		g_material_textures[i].texture = (textures && i < texture_count) ? (const char*) textures + (size_t) stride_bytes * i : nullptr;
 }
 
 // The 256-byte per_frame_constants_t block (main.h:537-553): std140 + row_major, so matrices arrive as rows.

@@ -81,6 +81,14 @@ typedef struct orc_material_s {
 	float normal_rg[2];
 } orc_material_t;
 
+/* A material texture as the product keeps it after loading (tables_scene.c decodes BC1 / BC5 blocks to 8-bit texels): every
+ * mip level, largest first, tightly packed, RGBA per texel. Sampled by orc_sample_texture_grad. */
+enum { ORC_TEXEL_RGBA32F = 0, ORC_TEXEL_RGBA8_UNORM = 1, ORC_TEXEL_RGBA8_SRGB = 2 };
+typedef struct orc_texture_s {
+	uint32_t format, width, height, mip_count;
+	const void* texels;
+} orc_texture_t;
+
 typedef struct orc_bvh_s orc_bvh_t;
 
 typedef struct orc_scene_s {
@@ -98,7 +106,19 @@ typedef struct orc_scene_s {
 	const uint16_t* ltc_rgba16;       /* layers*res*res*4 */
 	const uint16_t* ltc_rg16;         /* layers*res*res*2 */
 	orc_bvh_t* bvh;                   /* built by orc_build_bvh */
+	const orc_texture_t* textures;    /* NULL: flat materials (above); else 3 per material: base colour, specular, normal (scene.h:104-118) */
 } orc_scene_t;
+
+/* textureGrad with the sampler of scene.c:546-552 (linear mag / min / mip filters, repeat addressing) under the oracle's stated
+ * definition -- texture filtering is driver code, anisotropy (maxAnisotropy 16) is NOT modelled:
+ *   level of detail lambda = log2(max(|d(u W, v H)/dx|, |d(u W, v H)/dy|)) (Vulkan 1.2, 16.5.5-16.5.7, isotropic), clamped to
+ *   [0, mip_count - 1]; bilinear taps at levels floor(lambda) and floor(lambda) + 1 mixed by its fraction; a tap is
+ *   c00 + fx (c10 - c00) etc. at x = u w - 0.5 with repeat addressing, in fp32; 8-bit texels are c / 255 (correctly rounded),
+ *   sRGB texels go through the exact sRGB curve evaluated in double precision (alpha stays linear). log2 is correctly
+ *   rounded like the other transcendental functions. A texture whose texels are all equal returns exactly that texel. */
+void orc_sample_texture_grad(const orc_texture_t* texture, const float uv[2], const float ddx[2], const float ddy[2], float rgba[4]);
+/* table entry i: sRGB byte -> linear float (the table the product uploads is computed by the same formula) */
+float orc_srgb8_to_linear(uint32_t byte);
 
 /* ---- noise (noise_utility.glsl:26-95, math_utilities.h:50-57) ---- */
 uint32_t orc_wang_random_number(uint32_t seed);

@@ -26,6 +26,13 @@ def variant(light_sampling="reservoir", technique="ltc_cp", mis="optimal_clamped
                    min_vertices, max_vertices)
 
 
+class Texture(C.Structure):
+    _fields_ = [("format", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("mip_count", C.c_uint32), ("texels", C.c_void_p)]
+
+
+TEXEL = dict(rgba32f=0, rgba8_unorm=1, rgba8_srgb=2)
+
+
 class RisltcError(RuntimeError):
     pass
 
@@ -94,6 +101,20 @@ class Device:
     def upload_materials(self, constants):
         m = np.ascontiguousarray(constants, dtype=np.float32)
         _check(lib().risltc_cuda_upload_materials(self.h, _p(m), C.c_uint64(m.shape[0])))
+
+    def upload_textures(self, textures):
+        """textures: 3 per material, dicts {format: 'rgba32f' | 'rgba8_unorm' | 'rgba8_srgb', levels: [(h, w, 4) arrays, largest first]}."""
+        arr = (Texture * len(textures))()
+        keep = []
+        for i, tex in enumerate(textures):
+            dtype = np.float32 if tex["format"] == "rgba32f" else np.uint8
+            buf = np.concatenate([np.ascontiguousarray(l, dtype=dtype).reshape(-1) for l in tex["levels"]])
+            keep.append(buf)
+            arr[i].format = TEXEL[tex["format"]]
+            arr[i].height, arr[i].width = tex["levels"][0].shape[:2]
+            arr[i].mip_count = len(tex["levels"])
+            arr[i].texels = buf.ctypes.data
+        _check(lib().risltc_cuda_upload_textures(self.h, arr, C.c_uint64(len(textures))))
 
     def upload_lights(self, records):
         r = np.ascontiguousarray(records, dtype=np.float32)

@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@ struct risltc_device_s {
 	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };   // [0] batch start, [4] batch end
 	// scene
 	uint2* positions = nullptr; ushort4* normals_uv = nullptr; uint8_t* material_indices = nullptr;
+	TextureDesc* textures = nullptr; unsigned char* texels = nullptr; float* srgb_table = nullptr;
 	float4* materials = nullptr; float4* lights = nullptr; float4* lights_tri = nullptr; ushort4* ltc_rgba = nullptr; ushort2* ltc_rg = nullptr;
 	BvhNode* nodes = nullptr; BvhTri* tris = nullptr; Qbvh4Node* nodes4 = nullptr;
 	SceneView view = {};
@@ -71,7 +73,14 @@ struct risltc_device_s {
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel, two CTAs per SM: 384 (80 registers), 320 (96) or 256 (128)
 	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
 	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
-	uint32_t tri_vote = 16;       // lanes that must have a triangle waiting before trace_kernel runs its triangle track
+	// lanes that must have a triangle waiting before the shadow-ray kernel runs its triangle track. Few occluded rays (C2: 27 %):
+	// a well filled triangle track (8) wins; mostly occluded rays in a deep tree (C4: 93 %): testing the first triangle at once
+	// (1) ends them ~10 % of their node visits earlier. Unless RISLTC_TRI_VOTE pins it, the first two frames after a scene
+	// upload run one candidate each, timed with events, and the faster is kept (the image does not depend on it).
+	uint32_t tri_vote = 8;
+	uint32_t trace_tune = 0;      // 0, 1: time candidate 0 / 1 next, 2: both in flight, 3: decided
+	bool trace_pinned = false;
+	cudaEvent_t trace_tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	unsigned long long launches = 0;
 	bool timed = false;
 	// per-frame events of the last batch: RL_FRAME_EVENTS per frame (before (1), after (1), after (2a), after (2b) = after (2), after (3), after (4))
@@ -121,7 +130,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	d->raster.ticket = (unsigned int*) (d->raster.counter + 1);
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
-	if (const char* e = getenv("RISLTC_TRI_VOTE")) d->tri_vote = (uint32_t) atoi(e);   // tuning knobs
+	if (const char* e = getenv("RISLTC_TRI_VOTE")) { d->tri_vote = (uint32_t) atoi(e); d->trace_pinned = true; d->trace_tune = 3u; }   // tuning knobs
+	for (auto& ev : d->trace_tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 256 || t == 320) ? (uint32_t) t : 384u; }
 	if (const char* e = getenv("RISLTC_WINNER")) d->winner_cr = strcmp(e, "cr") == 0;
 	if (const char* e = getenv("RISLTC_GBUFFER")) { d->gbuffer_kind = (strcmp(e, "bvh") == 0) ? 0u : 1u; d->gbuffer_tune = 3u; d->gbuffer_pinned = true; }
@@ -162,10 +172,12 @@ extern "C" void risltc_cuda_destroy_device(risltc_device_t* d) {
 	cudaSetDevice(d->ordinal);
 	if (d->stream) cudaStreamSynchronize(d->stream);
 	free_targets(d); free_scene(d);
+	cudaFree(d->textures); cudaFree(d->texels); cudaFree(d->srgb_table);
 	cudaFree(d->materials); cudaFree(d->lights); cudaFree(d->lights_tri); cudaFree(d->ltc_rgba); cudaFree(d->ltc_rg); cudaFree(d->px.counters); cudaFree(d->px.ticket); cudaFree(d->raster.items); cudaFree(d->raster.counter);
 	for (auto& ev : d->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->frame_events) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : d->tune_ev) if (ev) cudaEventDestroy(ev);
+	for (auto& ev : d->trace_tune_ev) if (ev) cudaEventDestroy(ev);
 	if (d->stream) cudaStreamDestroy(d->stream);
 	if (d->stream2) cudaStreamDestroy(d->stream2);
 	for (auto& ev : d->ev_resolved) if (ev) cudaEventDestroy(ev);
@@ -231,6 +243,7 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	d->view.positions = d->positions; d->view.normals_uv = d->normals_uv; d->view.material_indices = d->material_indices;
 	d->view.nodes = d->nodes; d->view.nodes4 = d->nodes4; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
 	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
+	if (!d->trace_pinned) d->trace_tune = 0;
 	return 0;
 }
 
@@ -248,6 +261,58 @@ extern "C" int risltc_cuda_upload_materials(risltc_device_t* d, const float* m, 
 	CU(cudaMalloc(&d->materials, packed.size() * sizeof(float4)));
 	CU(cudaMemcpy(d->materials, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
 	d->view.materials = d->materials;
+	cudaFree(d->textures); cudaFree(d->texels); d->textures = nullptr; d->texels = nullptr;   // flat materials replace textures
+	d->view.textures = nullptr; d->view.texels = nullptr;
+	return 0;
+}
+
+extern "C" int risltc_cuda_upload_textures(risltc_device_t* d, const risltc_texture_t* textures, uint64_t count) {
+	if (use(d)) return 1;
+	if (!textures || count == 0 || count % 3 != 0) return fail("upload_textures: three textures per material (base colour, specular, normal)", nullptr);
+	std::vector<TextureDesc> descs(count);
+	size_t total = 0;
+	for (uint64_t i = 0; i != count; ++i) {
+		const risltc_texture_t& t = textures[i];
+		if (!t.texels || t.width == 0 || t.height == 0 || t.mip_count == 0 || t.mip_count > 16 || t.format > RISLTC_TEXEL_RGBA8_SRGB)
+			return fail("upload_textures: a texture needs texels, a positive extent, 1..16 mip levels and a known texel format", nullptr);
+		size_t texel_count = 0;
+		uint32_t w = t.width, h = t.height;
+		for (uint32_t l = 0; l != t.mip_count; ++l) { texel_count += (size_t) w * h; w = (w > 1) ? w >> 1 : 1; h = (h > 1) ? h >> 1 : 1; }
+		total = (total + 15) & ~(size_t) 15;
+		descs[i].offset = total; descs[i].format = t.format; descs[i].width = t.width; descs[i].height = t.height; descs[i].levels = t.mip_count;
+		descs[i].pad[0] = descs[i].pad[1] = 0;
+		total += texel_count * (t.format == RISLTC_TEXEL_RGBA32F ? 16 : 4);
+	}
+	CU(cudaStreamSynchronize(d->stream));
+	cudaFree(d->textures); cudaFree(d->texels); d->textures = nullptr; d->texels = nullptr;
+	d->view.textures = nullptr; d->view.texels = nullptr;
+	std::vector<unsigned char> staging(total);
+	for (uint64_t i = 0; i != count; ++i) {
+		const size_t end = (i + 1 != count) ? (size_t) descs[i + 1].offset : total;
+		size_t bytes = 0;
+		uint32_t w = textures[i].width, h = textures[i].height;
+		for (uint32_t l = 0; l != textures[i].mip_count; ++l) { bytes += (size_t) w * h; w = (w > 1) ? w >> 1 : 1; h = (h > 1) ? h >> 1 : 1; }
+		bytes *= (textures[i].format == RISLTC_TEXEL_RGBA32F ? 16 : 4);
+		(void) end;
+		memcpy(staging.data() + descs[i].offset, textures[i].texels, bytes);
+	}
+	CU(cudaMalloc(&d->texels, total ? total : 16));
+	CU(cudaMemcpy(d->texels, staging.data(), total, cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&d->textures, count * sizeof(TextureDesc)));
+	CU(cudaMemcpy(d->textures, descs.data(), count * sizeof(TextureDesc), cudaMemcpyHostToDevice));
+	if (!d->srgb_table) {
+		// sRGB byte -> linear, the exact curve in double precision rounded once (the oracle computes the same table)
+		float table[256];
+		for (int i = 0; i != 256; ++i) {
+			const double c = (double) i / 255.0;
+			table[i] = (float) ((c <= 0.04045) ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+		}
+		CU(cudaMalloc(&d->srgb_table, sizeof(table)));
+		CU(cudaMemcpy(d->srgb_table, table, sizeof(table), cudaMemcpyHostToDevice));
+	}
+	d->view.textures = d->textures; d->view.texels = d->texels; d->view.srgb_table = d->srgb_table;
+	// the flat constants are not read while textures are bound, but render_frames checks that materials exist
+	if (!d->materials) { CU(cudaMalloc(&d->materials, 2 * sizeof(float4))); CU(cudaMemset(d->materials, 0, 2 * sizeof(float4))); d->view.materials = d->materials; }
 	return 0;
 }
 
@@ -516,7 +581,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
 		// while the G-buffer implementations are being timed the frames stay on one stream; afterwards they alternate
-		const uint32_t set = (overlap && d->gbuffer_tune == 3) ? (alternate++ & 1u) : 0u;
+		const uint32_t set = (overlap && d->gbuffer_tune == 3 && d->trace_tune == 3) ? (alternate++ & 1u) : 0u;
 		const PixelBuffers& px = set ? d->px2 : d->px;
 		const RasterBuffers& raster = set ? d->raster2 : d->raster;
 		cudaStream_t stream = set ? d->stream2 : d->stream;
@@ -557,9 +622,21 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			// (3) persistent any-hit traversal over all ray slots
 			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
 			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < d->trace4_resident) ? d->trace_ctas_per_sm : d->trace4_resident;
+			static const uint32_t vote_candidates[2] = { 8u, 1u };
+			if (d->trace_tune == 2) {
+				float ms[2] = { 0.0f, 0.0f };
+				CU(cudaEventSynchronize(d->trace_tune_ev[3]));
+				CU(cudaEventElapsedTime(&ms[0], d->trace_tune_ev[0], d->trace_tune_ev[1]));
+				CU(cudaEventElapsedTime(&ms[1], d->trace_tune_ev[2], d->trace_tune_ev[3]));
+				d->tri_vote = vote_candidates[(ms[1] < 0.97f * ms[0]) ? 1 : 0];
+				d->trace_tune = 3;
+			}
+			const uint32_t tuning = d->trace_tune;
+			if (tuning < 2) { d->tri_vote = vote_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
 			if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
 			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
+			if (tuning < 2) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
 			d->launches += 1;
 		}
 		CU(cudaEventRecord(fe[4], stream));

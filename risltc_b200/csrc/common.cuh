@@ -69,6 +69,16 @@ struct __align__(16) Qbvh4Node {
 };
 #define RL_Q4_EMPTY 0x7FFFFFFF
 
+// ---- material textures (scene.h:104-118: base colour, specular, normal per material), every mip level decoded to RGBA texels
+#define RL_TEXEL_RGBA32F 0u
+#define RL_TEXEL_RGBA8_UNORM 1u
+#define RL_TEXEL_RGBA8_SRGB 2u
+struct __align__(16) TextureDesc {
+	unsigned long long offset;   // of level 0 in SceneView::texels, in bytes; the smaller levels follow tightly packed
+	uint32_t format, width, height, levels;
+	uint32_t pad[2];
+};
+
 struct SceneView {
 	const uint2* positions;          // T*3 quantised positions (mesh_t.positions)
 	const ushort4* normals_uv;       // T*3
@@ -80,6 +90,9 @@ struct SceneView {
 	const ushort4* ltc_rgba; const ushort2* ltc_rg; uint32_t ltc_res, ltc_layers;
 	const BvhNode* nodes; const BvhTri* tris; uint32_t triangle_count;
 	const Qbvh4Node* nodes4;         // the same tree collapsed to four children per node (shadow rays)
+	const TextureDesc* textures;     // 3 per material, or null: flat materials (the `materials` constants)
+	const unsigned char* texels;
+	const float* srgb_table;         // 256 entries: sRGB byte -> linear
 };
 
 struct PixelBuffers {

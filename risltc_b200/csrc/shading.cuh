@@ -66,6 +66,57 @@ __device__ __forceinline__ float3 decode_normal(float ox, float oy) {
 	return normalize3(n);
 }
 
+// ------------------------------------------------------- material textures
+// textureGrad with the sampler of scene.c:546-552 under the definition stated in DESIGN.md (texture filtering is driver
+// code; the CPU oracle implements the same definition): isotropic level of detail from the larger of the two screen-space footprints, trilinear, repeat
+// addressing, taps as c00 + fx (c10 - c00). Same operations in the same order as the oracle: bit-identical results.
+__device__ __forceinline__ float4 texture_texel(const SceneView& s, const TextureDesc& t, size_t level_offset, uint32_t w, int x, int y) {
+	const size_t index = level_offset + (size_t) y * w + (size_t) x;
+	if (t.format == RL_TEXEL_RGBA32F) return __ldg((const float4*) (s.texels + t.offset) + index);
+	const uchar4 p = __ldg((const uchar4*) (s.texels + t.offset) + index);
+	if (t.format == RL_TEXEL_RGBA8_SRGB) return make_float4(__ldg(&s.srgb_table[p.x]), __ldg(&s.srgb_table[p.y]), __ldg(&s.srgb_table[p.z]), (float) p.w / 255.0f);
+	return make_float4((float) p.x / 255.0f, (float) p.y / 255.0f, (float) p.z / 255.0f, (float) p.w / 255.0f);
+}
+__device__ __forceinline__ int texture_wrap(float coordinate, int size) {
+	const float wrapped = coordinate - floorf(coordinate / (float) size) * (float) size;
+	const int i = (int) wrapped;
+	return (i >= size || i < 0) ? 0 : i;
+}
+__device__ float4 texture_bilinear(const SceneView& s, const TextureDesc& t, uint32_t level, float u, float v) {
+	size_t offset = 0;
+	uint32_t w = t.width, h = t.height;
+	for (uint32_t l = 0; l != level; ++l) { offset += (size_t) w * h; w = (w > 1u) ? w >> 1 : 1u; h = (h > 1u) ? h >> 1 : 1u; }
+	float x = u * (float) w - 0.5f, y = v * (float) h - 0.5f;
+	if (!(fabsf(x) < 1.0e9f)) x = 0.0f;
+	if (!(fabsf(y) < 1.0e9f)) y = 0.0f;
+	const float x0 = floorf(x), y0 = floorf(y), fx = x - x0, fy = y - y0;
+	const int ix0 = texture_wrap(x0, (int) w), ix1 = texture_wrap(x0 + 1.0f, (int) w), iy0 = texture_wrap(y0, (int) h), iy1 = texture_wrap(y0 + 1.0f, (int) h);
+	const float4 c00 = texture_texel(s, t, offset, w, ix0, iy0), c10 = texture_texel(s, t, offset, w, ix1, iy0);
+	const float4 c01 = texture_texel(s, t, offset, w, ix0, iy1), c11 = texture_texel(s, t, offset, w, ix1, iy1);
+	float4 r;
+	{ const float top = c00.x + fx * (c10.x - c00.x), bottom = c01.x + fx * (c11.x - c01.x); r.x = top + fy * (bottom - top); }
+	{ const float top = c00.y + fx * (c10.y - c00.y), bottom = c01.y + fx * (c11.y - c01.y); r.y = top + fy * (bottom - top); }
+	{ const float top = c00.z + fx * (c10.z - c00.z), bottom = c01.z + fx * (c11.z - c01.z); r.z = top + fy * (bottom - top); }
+	{ const float top = c00.w + fx * (c10.w - c00.w), bottom = c01.w + fx * (c11.w - c01.w); r.w = top + fy * (bottom - top); }
+	return r;
+}
+__device__ float4 texture_sample_grad(const SceneView& s, uint32_t texture_index, float2 uv, float2 ddx, float2 ddy) {
+	const TextureDesc t = s.textures[texture_index];
+	const float W = (float) t.width, H = (float) t.height;
+	const float ax = ddx.x * W, ay = ddx.y * H, bx = ddy.x * W, by = ddy.y * H;
+	const float rho_squared = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
+	float lambda = 0.0f;
+	if (rho_squared > 0.0f && rho_squared < 3.0e38f) lambda = 0.5f * (float) log2((double) rho_squared);   // correctly rounded, like the oracle
+	lambda = clampf(lambda, 0.0f, (float) (t.levels - 1u));
+	const float level = floorf(lambda), fraction = lambda - level;
+	float4 c = texture_bilinear(s, t, (uint32_t) level, uv.x, uv.y);
+	if (fraction > 0.0f && (uint32_t) level + 1u < t.levels) {
+		const float4 n = texture_bilinear(s, t, (uint32_t) level + 1u, uv.x, uv.y);
+		c = make_float4(c.x + fraction * (n.x - c.x), c.y + fraction * (n.y - c.y), c.z + fraction * (n.z - c.z), c.w + fraction * (n.w - c.w));
+	}
+	return c;
+}
+
 struct ShadingPoint {  // shading_data_t, brdfs.glsl:22-39
 	float3 position, normal, outgoing;
 	float lambert_outgoing;
@@ -73,8 +124,8 @@ struct ShadingPoint {  // shading_data_t, brdfs.glsl:22-39
 	float roughness;
 };
 
-// get_shading_data, shading_pass.frag.glsl:571-672, for flat-colour materials (the texture
-// derivative block :604-627 only feeds textureGrad and is dropped).
+// get_shading_data, shading_pass.frag.glsl:571-672. Scenes with flat materials (no texture objects) skip the screen-space
+// derivative block (:604-627), which only feeds the three textureGrad fetches (:629-633).
 __device__ ShadingPoint reconstruct_shading_point(const SceneView& s, const FrameUniforms& f, uint32_t prim, float3 ray_dir) {
 	ShadingPoint r;
 	float3 p[3], n[3]; float2 uv[3];
@@ -96,7 +147,40 @@ __device__ ShadingPoint reconstruct_shading_point(const SceneView& s, const Fram
 	r.position = mk3(fmaf(bx, p[0].x, fmaf(by, p[1].x, bz * p[2].x)), fmaf(bx, p[0].y, fmaf(by, p[1].y, bz * p[2].y)), fmaf(bx, p[0].z, fmaf(by, p[1].z, bz * p[2].z)));
 	float3 ng = normalize3(mk3(fmaf(bx, n[0].x, fmaf(by, n[1].x, bz * n[2].x)), fmaf(bx, n[0].y, fmaf(by, n[1].y, bz * n[2].y)), fmaf(bx, n[0].z, fmaf(by, n[1].z, bz * n[2].z))));
 	uint32_t mat = __ldg(&s.material_indices[prim]);
-	float4 m0 = __ldg(&s.materials[2 * mat]), m1 = __ldg(&s.materials[2 * mat + 1]);
+	float4 m0, m1;   // {base colour rgb, -}, {linear roughness, metalicity, normal.r, normal.g}
+	if (s.textures) {
+		const float3 to0_ = sub3(origin, p[0]);
+		const float det_0_dir_edge_1 = dot3(to0_, ray_cross_e1);
+		const float3 edge_0_cross_0 = cross3(e0, to0_);
+		const float det_dir_edge_0_0 = dot3(ray_dir, edge_0_cross_0);
+		float3 bd[2];   // screen-space derivatives of the barycentrics, :604-617
+		#pragma unroll
+		for (int i = 0; i != 2; ++i) {
+			const float3 dd = mk3(f.pixel_to_ray[0][i], f.pixel_to_ray[1][i], f.pixel_to_ray[2][i]);
+			const float3 rc = cross3(dd, e1);
+			const float rcp_det_deriv = -dot3(e0, rc) * rcp_det * rcp_det;
+			const float d01 = dot3(to0_, rc);
+			bd[i].y = rcp_det_deriv * det_0_dir_edge_1 + rcp_det * d01;
+			const float d00 = dot3(dd, edge_0_cross_0);
+			bd[i].z = -rcp_det_deriv * det_dir_edge_0_0 - rcp_det * d00;
+			bd[i].x = -(bd[i].y + bd[i].z);
+		}
+		const float2 tc = mk2(fmaf(bx, uv[0].x, fmaf(by, uv[1].x, bz * uv[2].x)), fmaf(bx, uv[0].y, fmaf(by, uv[1].y, bz * uv[2].y)));
+		float2 dt[2];   // :622-627, accumulated from zero in the order j = 0, 1, 2
+		#pragma unroll
+		for (int i = 0; i != 2; ++i) {
+			dt[i] = mk2(0.0f, 0.0f);
+			dt[i].x += bd[i].x * uv[0].x; dt[i].y += bd[i].x * uv[0].y;
+			dt[i].x += bd[i].y * uv[1].x; dt[i].y += bd[i].y * uv[1].y;
+			dt[i].x += bd[i].z * uv[2].x; dt[i].y += bd[i].z * uv[2].y;
+		}
+		const float4 tb = texture_sample_grad(s, 3u * mat + 0u, tc, dt[0], dt[1]);
+		const float4 ts = texture_sample_grad(s, 3u * mat + 1u, tc, dt[0], dt[1]);
+		const float4 tn = texture_sample_grad(s, 3u * mat + 2u, tc, dt[0], dt[1]);
+		m0 = make_float4(tb.x, tb.y, tb.z, ts.x);
+		m1 = make_float4(ts.y, ts.z, tn.x, tn.y);
+	}
+	else { m0 = __ldg(&s.materials[2 * mat]); m1 = __ldg(&s.materials[2 * mat + 1]); }
 	float3 base = mk3(m0.x, m0.y, m0.z);
 	float3 nts;
 	nts.x = fmaf(m1.z, 2.0f, -1.0f);

@@ -132,7 +132,150 @@ def write_vkt_rgba32f(path, image):
         f.write(struct.pack("<I", EOF_MARKER))
 
 
-def read_vkt(path):
+VK_FORMAT_BC1_RGB_UNORM_BLOCK, VK_FORMAT_BC1_RGB_SRGB_BLOCK, VK_FORMAT_BC5_UNORM_BLOCK = 131, 132, 141
+
+
+def _blocks(level):
+    """(H, W, C) uint8 -> (blocks_y, blocks_x, 16, C) with edge texels repeated into partial blocks."""
+    h, w, c = level.shape
+    H, W = (h + 3) // 4 * 4, (w + 3) // 4 * 4
+    padded = np.zeros((H, W, c), dtype=np.uint8)
+    padded[:h, :w] = level
+    padded[h:, :w] = level[h - 1:h, :]
+    padded[:, w:] = padded[:, w - 1:w]
+    return padded.reshape(H // 4, 4, W // 4, 4, c).transpose(0, 2, 1, 3, 4).reshape(H // 4, W // 4, 16, c)
+
+
+def bc1_palette(c0, c1):
+    """(..., 4, 3) uint8 palette of BC1_RGB blocks with endpoints c0, c1 (uint16 RGB565): the decode rule of the host loader
+    (host/tables_scene.c): endpoints by bit replication, interpolated entries rounded to the nearest 8-bit value."""
+    def expand(c):
+        r, g, b = (c >> 11) & 31, (c >> 5) & 63, c & 31
+        return np.stack([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], axis=-1).astype(np.uint32)
+    e0, e1 = expand(c0.astype(np.uint32)), expand(c1.astype(np.uint32))
+    four = (c0 > c1)[..., None]
+    p2 = np.where(four, (2 * e0 + e1 + 1) // 3, (e0 + e1 + 1) // 2)
+    p3 = np.where(four, (e0 + 2 * e1 + 1) // 3, 0)
+    return np.stack([e0, e1, p2, p3], axis=-2).astype(np.uint8)
+
+
+def encode_bc1(level):
+    """(H, W, >=3) uint8 -> BC1_RGB blocks (bytes). Endpoints = the block's bounding box corners in RGB565, every texel takes
+    the nearest palette entry: simple, deterministic, good enough for test assets."""
+    b = _blocks(level[..., :3]).astype(np.int32)
+    lo, hi = b.min(axis=2), b.max(axis=2)
+
+    def pack565(c):
+        return (((c[..., 0] >> 3) << 11) | ((c[..., 1] >> 2) << 5) | (c[..., 2] >> 3)).astype(np.uint16)
+    c0, c1 = pack565(hi), pack565(lo)
+    swap = c0 < c1
+    c0, c1 = np.where(swap, c1, c0), np.where(swap, c0, c1)       # c0 >= c1; equal endpoints select the 3-colour mode, whose entries 0 and 1 coincide
+    pal = bc1_palette(c0, c1).astype(np.int32)                    # (by, bx, 4, 3)
+    usable = np.where((c0 > c1)[..., None], 4, 2)                 # in 3-colour mode avoid the black entry
+    d = ((b[:, :, :, None, :] - pal[:, :, None, :, :]) ** 2).sum(axis=-1)       # (by, bx, 16, 4)
+    d = np.where(np.arange(4)[None, None, None, :] < usable[..., None], d, 1 << 30)
+    idx = d.argmin(axis=-1).astype(np.uint32)                     # (by, bx, 16)
+    bits = (idx << (2 * np.arange(16, dtype=np.uint32))).sum(axis=-1).astype(np.uint32)
+    out = np.zeros(c0.shape + (8,), dtype=np.uint8)
+    out[..., 0] = c0 & 255; out[..., 1] = c0 >> 8; out[..., 2] = c1 & 255; out[..., 3] = c1 >> 8
+    for k in range(4):
+        out[..., 4 + k] = (bits >> (8 * k)) & 255
+    return out.tobytes()
+
+
+def bc4_palette(e0, e1):
+    e0, e1 = e0.astype(np.uint32), e1.astype(np.uint32)
+    eight = e0 > e1
+    pal = [e0, e1]
+    for k in range(1, 7):
+        a = ((7 - k) * e0 + k * e1 + 3) // 7
+        if k <= 4:
+            b = ((5 - k) * e0 + k * e1 + 2) // 5
+        else:
+            b = np.zeros_like(e0) if k == 5 else np.full_like(e0, 255)
+        pal.append(np.where(eight, a, b))
+    return np.stack(pal, axis=-1).astype(np.uint8)
+
+
+def _encode_bc4(channel_blocks):
+    b = channel_blocks.astype(np.int32)                           # (by, bx, 16)
+    e0, e1 = b.max(axis=2).astype(np.uint8), b.min(axis=2).astype(np.uint8)     # e0 >= e1; equal: 6-value mode, entries 0 / 1 coincide
+    pal = bc4_palette(e0, e1).astype(np.int32)
+    usable = np.where((e0 > e1)[..., None], 8, 2)
+    d = np.abs(b[..., None] - pal[:, :, None, :])
+    d = np.where(np.arange(8)[None, None, None, :] < usable[..., None], d, 1 << 30)
+    idx = d.argmin(axis=-1).astype(np.uint64)
+    bits = (idx << (3 * np.arange(16, dtype=np.uint64))).sum(axis=-1).astype(np.uint64)
+    out = np.zeros(e0.shape + (8,), dtype=np.uint8)
+    out[..., 0] = e0; out[..., 1] = e1
+    for k in range(6):
+        out[..., 2 + k] = (bits >> np.uint64(8 * k)) & np.uint64(255)
+    return out
+
+
+def encode_bc5(level):
+    """(H, W, >=2) uint8 -> BC5 blocks (red BC4 block, green BC4 block)."""
+    b = _blocks(level[..., :2])
+    return np.concatenate([_encode_bc4(b[..., 0]), _encode_bc4(b[..., 1])], axis=-1).tobytes()
+
+
+def decode_bc1(data, w, h):
+    """numpy decoder of BC1_RGB blocks -> (h, w, 4) uint8; the independent check of the host loader's decoder."""
+    by, bx = (h + 3) // 4, (w + 3) // 4
+    raw = np.frombuffer(data, np.uint8, by * bx * 8).reshape(by, bx, 8).astype(np.uint32)
+    c0, c1 = raw[..., 0] | (raw[..., 1] << 8), raw[..., 2] | (raw[..., 3] << 8)
+    pal = bc1_palette(c0, c1)
+    bits = raw[..., 4] | (raw[..., 5] << 8) | (raw[..., 6] << 16) | (raw[..., 7] << 24)
+    idx = (bits[..., None] >> (2 * np.arange(16, dtype=np.uint32))) & 3
+    tex = np.take_along_axis(pal, idx[..., None].astype(np.int64).repeat(3, axis=-1), axis=2)      # (by, bx, 16, 3)
+    img = tex.reshape(by, bx, 4, 4, 3).transpose(0, 2, 1, 3, 4).reshape(by * 4, bx * 4, 3)[:h, :w]
+    return np.concatenate([img, np.full((h, w, 1), 255, np.uint8)], axis=-1)
+
+
+def _decode_bc4(raw):
+    pal = bc4_palette(raw[..., 0].astype(np.uint8), raw[..., 1].astype(np.uint8))
+    bits = np.zeros(raw.shape[:2], dtype=np.uint64)
+    for k in range(6):
+        bits |= raw[..., 2 + k].astype(np.uint64) << np.uint64(8 * k)
+    idx = (bits[..., None] >> (3 * np.arange(16, dtype=np.uint64))) & np.uint64(7)
+    return np.take_along_axis(pal, idx.astype(np.int64), axis=2)
+
+
+def decode_bc5(data, w, h):
+    by, bx = (h + 3) // 4, (w + 3) // 4
+    raw = np.frombuffer(data, np.uint8, by * bx * 16).reshape(by, bx, 16)
+    r, g = _decode_bc4(raw[..., :8]), _decode_bc4(raw[..., 8:])
+    img = np.stack([r, g, np.zeros_like(r), np.full_like(r, 255)], axis=-1)
+    return img.reshape(by, bx, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(by * 4, bx * 4, 4)[:h, :w]
+
+
+def write_vkt(path, levels, vk_format):
+    """Mip-mapped texture in the layout of tools/texture_conversion/main.c:41-63. levels: (h, w, 4) arrays, largest first;
+    vk_format 109 (RGBA32F, float32 levels), 131 / 132 (BC1 RGB UNORM / SRGB, uint8 levels) or 141 (BC5, uint8 levels)."""
+    chunks = []
+    for level in levels:
+        if vk_format == VK_FORMAT_R32G32B32A32_SFLOAT:
+            chunks.append(np.ascontiguousarray(level, dtype="<f4").tobytes())
+        elif vk_format in (VK_FORMAT_BC1_RGB_UNORM_BLOCK, VK_FORMAT_BC1_RGB_SRGB_BLOCK):
+            chunks.append(encode_bc1(np.asarray(level, dtype=np.uint8)))
+        elif vk_format == VK_FORMAT_BC5_UNORM_BLOCK:
+            chunks.append(encode_bc5(np.asarray(level, dtype=np.uint8)))
+        else:
+            raise ValueError(f"VkFormat {vk_format} is not written")
+    payload = b"".join(chunks)
+    h, w = levels[0].shape[:2]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<IIIIIIQ", VKT_MARKER, 1, len(levels), w, h, vk_format, len(payload)))
+        offset = 0
+        for level, chunk in zip(levels, chunks):
+            f.write(struct.pack("<IIQQ", level.shape[1], level.shape[0], len(chunk), offset))
+            offset += len(chunk)
+        f.write(payload)
+        f.write(struct.pack("<I", EOF_MARKER))
+
+
+def read_vkt(path, with_format=False):
+    """All mip levels of a .vkt texture as (h, w, 4) arrays: float32 for RGBA32F, uint8 (decoded blocks) for BC1 / BC5."""
     data = Path(path).read_bytes()
     marker, version, mips, w, h, fmt, size = struct.unpack_from("<IIIIIIQ", data, 0)
     if marker != VKT_MARKER or version != 1:
@@ -145,12 +288,17 @@ def read_vkt(path):
     (eof,) = struct.unpack_from("<I", data, off + size)
     if eof != EOF_MARKER:
         raise ValueError(f"{path}: texture data is not followed by the end-of-file marker")
-    if fmt != VK_FORMAT_R32G32B32A32_SFLOAT:
-        raise NotImplementedError(f"{path}: VkFormat {fmt} (block-compressed textures are not decoded yet)")
     out = []
     for (mw, mh, msize, moff) in headers:
-        out.append(np.frombuffer(payload, "<f4", mw * mh * 4, moff).reshape(mh, mw, 4).copy())
-    return out
+        if fmt == VK_FORMAT_R32G32B32A32_SFLOAT:
+            out.append(np.frombuffer(payload, "<f4", mw * mh * 4, moff).reshape(mh, mw, 4).copy())
+        elif fmt in (VK_FORMAT_BC1_RGB_UNORM_BLOCK, VK_FORMAT_BC1_RGB_SRGB_BLOCK):
+            out.append(decode_bc1(payload[moff:moff + msize], mw, mh))
+        elif fmt == VK_FORMAT_BC5_UNORM_BLOCK:
+            out.append(decode_bc5(payload[moff:moff + msize], mw, mh))
+        else:
+            raise NotImplementedError(f"{path}: VkFormat {fmt}")
+    return (out, fmt) if with_format else out
 
 
 # ----------------------------------------------------------------- fit*.dat

@@ -48,7 +48,14 @@ def write_scene_files(scene, directory, ltc_fits=None, name=None):
     tex.mkdir(parents=True, exist_ok=True)
     vks = directory / f"{name}.vks"
     formats.write_vks(vks, scene["mesh"])
-    for m in scene["materials"]:
+    if scene.get("textures") is not None:
+        # the formats the reference's texture conversion tool produces: BC1 sRGB base colour, BC1 specular, BC5 normal
+        for i, m in enumerate(scene["materials"]):
+            base, spec, nrm = scene["textures"][3 * i:3 * i + 3]
+            formats.write_vkt(tex / f"{m['name']}_BaseColor.vkt", base["levels"], formats.VK_FORMAT_BC1_RGB_SRGB_BLOCK if base["format"] == "rgba8_srgb" else formats.VK_FORMAT_BC1_RGB_UNORM_BLOCK)
+            formats.write_vkt(tex / f"{m['name']}_Specular.vkt", spec["levels"], formats.VK_FORMAT_BC1_RGB_UNORM_BLOCK)
+            formats.write_vkt(tex / f"{m['name']}_Normal.vkt", nrm["levels"], formats.VK_FORMAT_BC5_UNORM_BLOCK)
+    for m in (scene["materials"] if scene.get("textures") is None else []):
         base = np.array([[list(m["base_color"]) + [1.0]]], dtype=np.float32)
         spec = np.array([[[1.0, m["roughness"], m["metalicity"], 1.0]]], dtype=np.float32)
         nrm = np.array([[[0.5, 0.5, 1.0, 1.0]]], dtype=np.float32)

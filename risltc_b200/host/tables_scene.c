@@ -151,9 +151,76 @@ void destroy_scene(scene_t* scene, const device_t* device) {
 	memset(scene, 0, sizeof(*scene));
 }
 
-/* One *.vkt texture (textures.c:95-172, header tools/texture_conversion/main.c:41-63): keeps mip 0.
- * Only VK_FORMAT_R32G32B32A32_SFLOAT payloads are decoded in this round; the block-compressed
- * formats of downloaded assets (BC1 = 131/132, BC5 = 141) are reported as unsupported. */
+/* ---- block-compressed texels. The reference hands BC1 / BC5 blocks to the texture units; here they are decoded once at load
+ * time. Block layouts are those of the Vulkan / D3D specification; interpolated palette entries are the exact rational
+ * values rounded to the nearest 8-bit value (hardware decoders differ from one another in the last bit here). */
+static void decode_bc1_block(const uint8_t block[8], uint8_t rgba[16][4]) {
+	const uint32_t c0 = block[0] | ((uint32_t) block[1] << 8), c1 = block[2] | ((uint32_t) block[3] << 8);
+	uint32_t palette[4][3];
+	const uint32_t endpoints[2] = { c0, c1 };
+	for (int e = 0; e != 2; ++e) {
+		const uint32_t r = (endpoints[e] >> 11) & 31u, g = (endpoints[e] >> 5) & 63u, b = endpoints[e] & 31u;
+		palette[e][0] = (r << 3) | (r >> 2); palette[e][1] = (g << 2) | (g >> 4); palette[e][2] = (b << 3) | (b >> 2);
+	}
+	for (int k = 0; k != 3; ++k) {
+		if (c0 > c1) {
+			palette[2][k] = (2u * palette[0][k] + palette[1][k] + 1u) / 3u;
+			palette[3][k] = (palette[0][k] + 2u * palette[1][k] + 1u) / 3u;
+		}
+		else {
+			palette[2][k] = (palette[0][k] + palette[1][k] + 1u) / 2u;
+			palette[3][k] = 0u;   /* BC1_RGB: the transparent entry reads as opaque black */
+		}
+	}
+	const uint32_t indices = block[4] | ((uint32_t) block[5] << 8) | ((uint32_t) block[6] << 16) | ((uint32_t) block[7] << 24);
+	for (int i = 0; i != 16; ++i) {
+		const uint32_t* c = palette[(indices >> (2 * i)) & 3u];
+		rgba[i][0] = (uint8_t) c[0]; rgba[i][1] = (uint8_t) c[1]; rgba[i][2] = (uint8_t) c[2]; rgba[i][3] = 255;
+	}
+}
+
+static void decode_bc4_block(const uint8_t block[8], uint8_t values[16]) {
+	const uint32_t e0 = block[0], e1 = block[1];
+	uint32_t palette[8] = { e0, e1, 0, 0, 0, 0, 0, 0 };
+	if (e0 > e1)
+		for (uint32_t k = 1; k != 7; ++k) palette[k + 1] = ((7u - k) * e0 + k * e1 + 3u) / 7u;
+	else {
+		for (uint32_t k = 1; k != 5; ++k) palette[k + 1] = ((5u - k) * e0 + k * e1 + 2u) / 5u;
+		palette[6] = 0u; palette[7] = 255u;
+	}
+	uint64_t indices = 0;
+	for (int k = 0; k != 6; ++k) indices |= (uint64_t) block[2 + k] << (8 * k);
+	for (int i = 0; i != 16; ++i) values[i] = (uint8_t) palette[(indices >> (3 * i)) & 7u];
+}
+
+/* One mip level of width x height texels from BC1 (8-byte blocks) or BC5 (two BC4 blocks: red, green) to RGBA8 */
+static void decode_block_compressed_level(uint8_t* rgba, const uint8_t* blocks, uint32_t width, uint32_t height, int bc5) {
+	const uint32_t blocks_x = (width + 3) / 4, blocks_y = (height + 3) / 4, block_size = bc5 ? 16u : 8u;
+	for (uint32_t by = 0; by != blocks_y; ++by)
+		for (uint32_t bx = 0; bx != blocks_x; ++bx) {
+			const uint8_t* block = blocks + ((size_t) by * blocks_x + bx) * block_size;
+			uint8_t texels[16][4];
+			if (bc5) {
+				uint8_t red[16], green[16];
+				decode_bc4_block(block, red); decode_bc4_block(block + 8, green);
+				for (int i = 0; i != 16; ++i) { texels[i][0] = red[i]; texels[i][1] = green[i]; texels[i][2] = 0; texels[i][3] = 255; }
+			}
+			else decode_bc1_block(block, texels);
+			for (uint32_t y = 0; y != 4; ++y)
+				for (uint32_t x = 0; x != 4; ++x) {
+					const uint32_t px = 4 * bx + x, py = 4 * by + y;
+					if (px < width && py < height) memcpy(rgba + 4 * ((size_t) py * width + px), texels[4 * y + x], 4);
+				}
+		}
+}
+
+/* Exposed for tests: decode `width` x `height` texels of BC1 (bc5 == 0) or BC5 (bc5 != 0) blocks to RGBA8 */
+void decode_block_compressed_texels(uint8_t* rgba, const uint8_t* blocks, uint32_t width, uint32_t height, int bc5) {
+	decode_block_compressed_level(rgba, blocks, width, height, bc5);
+}
+
+/* One *.vkt texture (textures.c:95-172, header tools/texture_conversion/main.c:41-63) with its whole mip chain. The formats the
+ * texture conversion tool writes are accepted: RGBA32F as it is, BC1 (UNORM / SRGB) and BC5 decoded to RGBA8. */
 static int load_vkt_texture(image_t* image, const char* file_path) {
 	FILE* file = fopen(file_path, "rb");
 	if (!file) {
@@ -166,15 +233,20 @@ static int load_vkt_texture(image_t* image, const char* file_path) {
 		fclose(file);
 		return 1;
 	}
-	uint32_t mipmap_count = head[2];
+	const uint32_t mipmap_count = head[2];
 	image->width = head[3]; image->height = head[4]; image->format = (VkFormat) head[5]; image->layers = 1;
-	uint64_t mip0_size = 0, mip0_offset = 0;
-	for (uint32_t k = 0; k != mipmap_count; ++k) {
-		uint32_t resolution[2]; uint64_t size_offset[2];
-		if (fread(resolution, sizeof(uint32_t), 2, file) != 2 || fread(size_offset, sizeof(uint64_t), 2, file) != 2) { fclose(file); return 1; }
-		if (k == 0) { mip0_size = size_offset[0]; mip0_offset = size_offset[1]; }
+	if (mipmap_count == 0 || mipmap_count > 32 || image->width == 0 || image->height == 0) {
+		printf("The texture at path %s has an invalid header (%u mipmaps of %ux%u).\n", file_path, mipmap_count, image->width, image->height);
+		fclose(file);
+		return 1;
 	}
-	char* payload = (char*) malloc(payload_size ? payload_size : 1);
+	uint32_t resolutions[32][2]; uint64_t sizes[32], offsets[32];
+	for (uint32_t k = 0; k != mipmap_count; ++k) {
+		uint64_t size_offset[2];
+		if (fread(resolutions[k], sizeof(uint32_t), 2, file) != 2 || fread(size_offset, sizeof(uint64_t), 2, file) != 2) { fclose(file); return 1; }
+		sizes[k] = size_offset[0]; offsets[k] = size_offset[1];
+	}
+	uint8_t* payload = (uint8_t*) malloc(payload_size ? payload_size : 1);
 	uint32_t eof_marker = 0;
 	if (fread(payload, 1, payload_size, file) != payload_size || fread(&eof_marker, sizeof(eof_marker), 1, file) != 1 || eof_marker != 0xE0FE0F) {
 		printf("The texture file at path %s seems to be invalid. The texture data is not followed by the expected end of file marker.\n", file_path);
@@ -182,16 +254,39 @@ static int load_vkt_texture(image_t* image, const char* file_path) {
 		return 1;
 	}
 	fclose(file);
-	if (image->format != VK_FORMAT_R32G32B32A32_SFLOAT) {
-		printf("The texture at path %s uses VkFormat %d; only uncompressed RGBA32F (109) textures are supported so far.\n", file_path, (int) image->format);
+	const int bc1 = image->format == VK_FORMAT_BC1_RGB_UNORM_BLOCK || image->format == VK_FORMAT_BC1_RGB_SRGB_BLOCK, bc5 = image->format == VK_FORMAT_BC5_UNORM_BLOCK;
+	if (!bc1 && !bc5 && image->format != VK_FORMAT_R32G32B32A32_SFLOAT) {
+		printf("The texture at path %s uses VkFormat %d; supported are RGBA32F (109), BC1 (131, 132) and BC5 (141).\n", file_path, (int) image->format);
 		free(payload);
 		return 1;
 	}
-	image->host_size = (size_t) mip0_size;
+	const size_t texel_size = (bc1 || bc5) ? 4 : 16;
+	size_t texel_count = 0;
+	for (uint32_t k = 0; k != mipmap_count; ++k) texel_count += (size_t) resolutions[k][0] * resolutions[k][1];
+	image->mip_count = mipmap_count;
+	image->texel_format = (bc1 || bc5) ? ((image->format == VK_FORMAT_BC1_RGB_SRGB_BLOCK) ? RISLTC_TEXEL_RGBA8_SRGB : RISLTC_TEXEL_RGBA8_UNORM) : RISLTC_TEXEL_RGBA32F;
+	image->host_size = texel_count * texel_size;
 	image->host_data = malloc(image->host_size ? image->host_size : 1);
-	memcpy(image->host_data, payload + mip0_offset, image->host_size);
+	size_t cursor = 0;
+	int result = 0;
+	for (uint32_t k = 0; k != mipmap_count && !result; ++k) {
+		const uint32_t w = resolutions[k][0], h = resolutions[k][1];
+		/* the sampler assumes the usual chain: every level half the previous one, rounded down, at least 1 */
+		const uint32_t expected_w = (image->width >> k) ? (image->width >> k) : 1, expected_h = (image->height >> k) ? (image->height >> k) : 1;
+		const size_t stored = (bc1 || bc5) ? (size_t) ((w + 3) / 4) * ((h + 3) / 4) * (bc5 ? 16 : 8) : (size_t) w * h * 16;
+		if (w != expected_w || h != expected_h || offsets[k] + stored > payload_size || sizes[k] < stored) {
+			printf("The texture at path %s has an unexpected mipmap %u (%ux%u, %llu bytes).\n", file_path, k, w, h, (unsigned long long) sizes[k]);
+			result = 1;
+			break;
+		}
+		uint8_t* level = (uint8_t*) image->host_data + cursor;
+		if (bc1 || bc5) decode_block_compressed_level(level, payload + offsets[k], w, h, bc5);
+		else memcpy(level, payload + offsets[k], (size_t) w * h * 16);
+		cursor += (size_t) w * h * texel_size;
+	}
 	free(payload);
-	return 0;
+	if (result) { free(image->host_data); image->host_data = NULL; image->host_size = 0; }
+	return result;
 }
 
 int load_scene(scene_t* scene, const device_t* device, const char* file_path, const char* texture_path, VkBool32 request_acceleration_structure) {
@@ -276,28 +371,39 @@ int load_scene(scene_t* scene, const device_t* device, const char* file_path, co
 	scene->materials.textures.image_count = texture_count;
 	scene->materials.textures.images = (image_t*) calloc(texture_count ? texture_count : 1, sizeof(image_t));
 	float* constants = (float*) calloc(scene->materials.material_count ? scene->materials.material_count : 1, sizeof(float) * 8);
-	int result = 0;
+	int result = 0, flat = 1;
 	for (uint64_t i = 0; i != scene->materials.material_count && !result; ++i) {
 		for (uint32_t j = 0; j != material_texture_count && !result; ++j) {
 			char* name = join_strings(texture_path, "/", scene->materials.material_names[i], "_");
 			char* path = join_strings(name, get_material_texture_suffix((material_texture_type_t) j), ".vkt", "");
 			image_t* image = &scene->materials.textures.images[i * material_texture_count + j];
 			result = load_vkt_texture(image, path);
-			if (!result) {
-				/* flat-colour materials: the texel every fetch of shading_pass.frag.glsl:630-633 returns */
+			if (!result && image->texel_format == RISLTC_TEXEL_RGBA32F && image->width * image->height == 1) {
+				/* a flat material: the texel every fetch of shading_pass.frag.glsl:630-633 returns */
 				const float* texel = (const float*) image->host_data;
 				float* c = constants + 8 * i;
 				if (j == material_texture_type_base_color) { c[0] = texel[0]; c[1] = texel[1]; c[2] = texel[2]; }
 				else if (j == material_texture_type_specular) { c[3] = texel[0]; c[4] = texel[1]; c[5] = texel[2]; }
 				else { c[6] = texel[0]; c[7] = texel[1]; }
-				if (image->width * image->height != 1)
-					printf("Note: the texture at path %s has %ux%u texels; only its first texel is used (flat-colour materials).\n", path, image->width, image->height);
 			}
+			else flat = 0;
 			free(name); free(path);
 		}
 	}
-	if (!result && device && device->cuda && scene->materials.material_count)
-		result = risltc_cuda_upload_materials(device->cuda, constants, scene->materials.material_count);
+	if (!result && device && device->cuda && scene->materials.material_count) {
+		/* scenes whose materials are all flat keep the constant path of the kernels; any real texture switches to textureGrad */
+		if (flat) result = risltc_cuda_upload_materials(device->cuda, constants, scene->materials.material_count);
+		else {
+			risltc_texture_t* textures = (risltc_texture_t*) calloc(texture_count, sizeof(risltc_texture_t));
+			for (uint32_t i = 0; i != texture_count; ++i) {
+				const image_t* image = &scene->materials.textures.images[i];
+				textures[i].format = image->texel_format; textures[i].width = image->width; textures[i].height = image->height;
+				textures[i].mip_count = image->mip_count; textures[i].texels = image->host_data;
+			}
+			result = risltc_cuda_upload_textures(device->cuda, textures, texture_count);
+			free(textures);
+		}
+	}
 	free(constants);
 	if (result) {
 		printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);

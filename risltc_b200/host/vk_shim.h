@@ -73,9 +73,11 @@ typedef struct image_s {
 	VkImageView view;
 	VkFormat format;
 	uint32_t width, height, layers;
-	/* Host copy of mip 0 / all layers (malloc), uploaded through the C ABI */
+	/* Host copy (malloc), uploaded through the C ABI: all layers of an array texture, or every mip level of a material
+	 * texture, largest first, decoded to RGBA texels of `texel_format` (RISLTC_TEXEL_*, include/risltc_cuda.h) */
 	void* host_data;
 	size_t host_size;
+	uint32_t mip_count, texel_format;
 } image_t;
 
 typedef struct images_s {

@@ -246,3 +246,68 @@ def material_constants(materials):
         out[i, 3:6] = [1.0, m["roughness"], m["metalicity"]]
         out[i, 6:8] = [0.5, 0.5]
     return out
+
+
+# -------------------------------------------------------------- material textures
+def _srgb_to_linear(b):
+    c = np.asarray(b, dtype=np.float64) / 255.0
+    return np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+
+
+def _linear_to_srgb8(x):
+    x = np.clip(np.asarray(x, dtype=np.float64), 0.0, 1.0)
+    s = np.where(x <= 0.0031308, 12.92 * x, 1.055 * x ** (1.0 / 2.4) - 0.055)
+    return np.asarray(np.floor(s * 255.0 + 0.5), dtype=np.uint8)
+
+
+def mip_chain(level0, srgb=False):
+    """All mip levels of an (H, W, 4) uint8 image down to 1x1 by 2x2 box filtering (in linear light for sRGB colour)."""
+    levels = [np.ascontiguousarray(level0, dtype=np.uint8)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1]
+        h, w = max(1, a.shape[0] // 2), max(1, a.shape[1] // 2)
+        lin = a.astype(np.float64) / 255.0
+        if srgb:
+            lin[..., :3] = _srgb_to_linear(a[..., :3])
+        lin = lin[:2 * h if a.shape[0] > 1 else 1, :2 * w if a.shape[1] > 1 else 1]
+        lin = lin.reshape(h, lin.shape[0] // h, w, lin.shape[1] // w, 4).mean(axis=(1, 3))
+        out = np.asarray(np.floor(lin * 255.0 + 0.5), dtype=np.uint8)
+        if srgb:
+            out[..., :3] = _linear_to_srgb8(lin[..., :3])
+        levels.append(out)
+    return levels
+
+
+def add_procedural_textures(scene, seed=1, size=64):
+    """Gives every material of `scene` three mip-mapped 8-bit textures like the reference's assets have (scene.h:104-118):
+    an sRGB checkerboard around its base colour, a specular map (occlusion, striped linear roughness, metalicity) and a
+    tangent-space normal map with round bumps. Stored in scene['textures'] (3 per material) as
+    {format: 'rgba8_srgb' | 'rgba8_unorm', levels: [...]}; risltc_b200.formats writes them as BC1 / BC5 .vkt files."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:size, 0:size]
+    textures = []
+    for m in scene["materials"]:
+        cells = int(rng.choice([4, 8]))
+        checker = ((x * cells // size) + (y * cells // size)) % 2
+        base = np.asarray(m["base_color"], dtype=np.float64)
+        other = np.clip(base * rng.uniform(0.35, 0.7) + rng.uniform(0.0, 0.15, 3), 0.0, 1.0)
+        colour = np.where(checker[..., None] == 0, base, other)
+        img = np.zeros((size, size, 4), dtype=np.uint8)
+        img[..., :3] = _linear_to_srgb8(colour); img[..., 3] = 255
+        textures.append(dict(format="rgba8_srgb", levels=mip_chain(img, srgb=True)))
+        stripes = 0.5 + 0.5 * np.sin(2.0 * np.pi * (x + 0.5) * int(rng.integers(2, 5)) / size)
+        rough = np.clip(m["roughness"] * (0.75 + 0.25 * stripes), 0.05, 1.0)
+        spec = np.zeros((size, size, 4), dtype=np.uint8)
+        spec[..., 0] = 255; spec[..., 1] = np.floor(rough * 255.0 + 0.5); spec[..., 2] = int(round(m["metalicity"] * 255.0)); spec[..., 3] = 255
+        textures.append(dict(format="rgba8_unorm", levels=mip_chain(spec)))
+        period = size // int(rng.choice([2, 4]))
+        px, py = ((x % period) + 0.5) / period - 0.5, ((y % period) + 0.5) / period - 0.5
+        bump = np.clip(0.2 - (px * px + py * py), 0.0, None)
+        gy, gx = np.gradient(bump * 6.0)
+        n = np.stack([-gx * period, -gy * period, np.ones_like(gx)], axis=-1)
+        n /= np.linalg.norm(n, axis=-1, keepdims=True)
+        nrm = np.zeros((size, size, 4), dtype=np.uint8)
+        nrm[..., :2] = np.floor((n[..., :2] * 0.5 + 0.5) * 255.0 + 0.5); nrm[..., 2] = 255; nrm[..., 3] = 255
+        textures.append(dict(format="rgba8_unorm", levels=mip_chain(nrm)))
+    scene["textures"] = textures
+    return scene

@@ -151,6 +151,18 @@ def frames():
             accum, vis, rays = r.render(cs)
             out[f"{name}.accum"] = accum; out[f"{name}.rays"] = np.uint64(rays)
             out[f"{k}.visibility"] = vis
+    # textured materials: mip-mapped 8-bit textures (sRGB base colour, specular, normal) sampled by the oracle's textureGrad
+    # (texture filtering is driver code); the compiled reference GLSL computes the texture-coordinate derivatives
+    scene = scenes.add_procedural_textures(scenes.many_light_room(12, 10, seed=3, width=W, height=H), seed=1, size=32)
+    osc = orc.OracleScene(scene, rgba, rg)
+    cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=16, ltc_layers=6) for f in range(F)]
+    out["scene_tex.constants"] = np.frombuffer(b"".join(bytes(C.string_at(C.byref(c), 256)) for c in cs), dtype=np.uint8).reshape(F, 256)
+    out["scene_tex.formats"] = np.array([orc.TEXEL[t["format"]] for t in scene["textures"]], dtype=np.uint32)
+    out["scene_tex.level_counts"] = np.array([len(t["levels"]) for t in scene["textures"]], dtype=np.uint32)
+    out["scene_tex.texels"] = np.concatenate([l.reshape(-1) for t in scene["textures"] for l in t["levels"]])
+    r = ref.RefShading("ris_ltc_v3"); r.bind(osc)
+    accum, vis, rays = r.render(cs)
+    out["scene_tex.accum"] = accum; out["scene_tex.rays"] = np.uint64(rays)
     np.savez_compressed(HERE / "frames.npz", **out)
     print("frames.npz", sum(np.asarray(v).nbytes for v in out.values()), "bytes raw")
 

@@ -9,6 +9,8 @@ pixels agreeing AT MATCHED SPP (1, 4 and 16 accumulated frames alike), where a p
 |a - b| <= 1e-3 max(|a|, |b|) + 1e-5 on every channel of the fp32 accumulation buffer. Both modes are
 gated at that tolerance or tighter (GATES below); every figure is also appended to gpurun_out/parity_log.txt, which is
 committed under profiles/ after a GPU session."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -343,3 +345,62 @@ def test_output_stage(ltc_tables, tmp_path):
     got = formats.read_hdr(tmp_path / "shot.hdr")
     assert np.all(np.abs(got - want) <= want.max(axis=-1, keepdims=True) * 2.0 ** -7 + 1e-30)
     assert (frames[0].max() == 255) and (frames[0].min() == 0)
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_textured_materials(device, ltc_tables, precision):
+    """Mip-mapped material textures (get_shading_data's derivative block and three textureGrad fetches,
+    shading_pass.frag.glsl:604-635) against the oracle under the stated filtering definition: exact mode bit for bit."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    W, H = 320, 180
+    scene = scenes.add_procedural_textures(scenes.many_light_room(32, 40, seed=3, width=W, height=H))
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(), api.variant(), W, H, 4, precision)
+    assert np.array_equal(vis, ref_vis)
+    check("textured materials, 32 lights 320x180", precision, got, ref, 4, counters, ref_rays)
+    flat = scenes.many_light_room(32, 40, seed=3, width=W, height=H)
+    flat_image = _render_both(device, flat, ltc_tables, orc.variant(), api.variant(), W, H, 4, precision)[3]
+    assert np.mean(np.any(got != flat_image, axis=-1)) > 0.5, "the textures have no effect"
+
+
+def test_textured_scene_through_the_host_layer(ltc_tables, tmp_path):
+    """Block-compressed *.vkt files (BC1 sRGB base colour, BC1 specular, BC5 normal, full mip chains; textures.c:95-241) through
+    load_scene render the same image as uploading the decoded texels directly, and as the oracle on those texels."""
+    from oracle import orc
+    from risltc_b200 import api, formats, host, scenes
+    fits, rgba, rg = ltc_tables
+    W, H = 200, 120
+    scene = scenes.add_procedural_textures(scenes.many_light_room(16, 20, seed=12, width=W, height=H), size=32)
+    idx = np.minimum(np.arange(51) * rgba.shape[0] // 51, rgba.shape[0] - 1)
+    fits51 = np.asarray(fits)[idx]
+    vks, tex, save = host.write_scene_files(scene, tmp_path, ltc_fits=fits51)
+    app = host.Application(tmp_path)
+    try:
+        app.load(vks, tex, save, W, H)
+        app.settings(accum=1)
+        app.reset(0)
+        app.render_frames(2)
+        got = app.device().read_accum()
+    finally:
+        app.close()
+    # what the files hold after lossy block compression, decoded by the independent numpy decoder
+    decoded = dict(scene)
+    decoded["textures"] = []
+    for i, m in enumerate(scene["materials"]):
+        for j, suffix in enumerate(("BaseColor", "Specular", "Normal")):
+            levels, fmt = formats.read_vkt(Path(tex) / f"{m['name']}_{suffix}.vkt", with_format=True)
+            decoded["textures"].append(dict(format="rgba8_srgb" if fmt == formats.VK_FORMAT_BC1_RGB_SRGB_BLOCK else "rgba8_unorm", levels=levels))
+    from risltc_b200 import ltc_fit
+    rgba51, rg51 = ltc_fit.quantize_fits(fits51)
+    osc = orc.OracleScene(decoded, rgba51, rg51)
+    cs = [orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba51.shape[1], ltc_layers=51) for f in range(2)]
+    want, _, _ = osc.render(cs, orc.variant())
+    check("textured scene through load_scene (BC1 / BC5 files)", "fast", got, want, 2)
+    dev = api.Device(0)
+    try:
+        setup_device(dev, decoded, rgba51, rg51, api.variant(), W, H, osc.records)
+        dev.render_frames(constants_bytes(cs))
+        direct = dev.read_accum()
+    finally:
+        dev.close()
+    assert np.array_equal(direct.view(np.uint32), got.view(np.uint32)), "host loader and direct upload of the decoded texels differ"

@@ -162,6 +162,39 @@ def test_hdr_writer(lib, tmp_path):
     assert np.allclose([px[0] * 2.0 ** e, px[1] * 2.0 ** e, px[2] * 2.0 ** e], [0.5, 2.0, 0.125], rtol=0.02)
 
 
+def test_block_compressed_textures(lib, tmp_path):
+    """tables_scene.c decodes BC1 / BC5 blocks (the formats of the reference's texture conversion tool,
+    tools/texture_conversion/main.c:32-38) exactly like the independent numpy decoder, partial blocks included; *.vkt files
+    with mip chains round-trip; the oracle's sampler returns a flat texture's texel exactly."""
+    from oracle import orc
+    from risltc_b200 import formats, scenes
+    rng = np.random.default_rng(3)
+    for bc5, (w, h) in ((0, (20, 12)), (1, (20, 12)), (0, (5, 7)), (1, (2, 1)), (0, (64, 64))):
+        n = ((w + 3) // 4) * ((h + 3) // 4) * (16 if bc5 else 8)
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        lib.decode_block_compressed_texels(out.ctypes.data_as(C.c_void_p), data, C.c_uint32(w), C.c_uint32(h), C.c_int(bc5))
+        assert np.array_equal(out, formats.decode_bc5(data, w, h) if bc5 else formats.decode_bc1(data, w, h)), (bc5, w, h)
+    scene = scenes.add_procedural_textures(scenes.many_light_room(4, 2, width=32, height=18), size=32)
+    base, spec, nrm = scene["textures"][:3]
+    for tex, fmt, channels, tolerance in ((base, formats.VK_FORMAT_BC1_RGB_SRGB_BLOCK, 3, 24), (spec, formats.VK_FORMAT_BC1_RGB_UNORM_BLOCK, 3, 24), (nrm, formats.VK_FORMAT_BC5_UNORM_BLOCK, 2, 20)):
+        path = tmp_path / "t.vkt"
+        formats.write_vkt(path, tex["levels"], fmt)
+        levels, got_fmt = formats.read_vkt(path, with_format=True)
+        assert got_fmt == fmt and [l.shape for l in levels] == [l.shape for l in tex["levels"]]
+        for a, b in zip(levels, tex["levels"]):
+            assert np.abs(a[..., :channels].astype(int) - b[..., :channels].astype(int)).max() <= tolerance
+    # sampler properties: a flat texture returns its texel exactly at any footprint; level of detail picks the 1x1 level
+    flat = dict(format="rgba32f", levels=[np.full((4, 4, 4), 0.3217, np.float32), np.full((2, 2, 4), 0.3217, np.float32), np.full((1, 1, 4), 0.3217, np.float32)])
+    for uv, dx in (((0.3, 0.9), 0.01), ((-3.7, 12.2), 0.2), ((0.5, 0.5), 7.0)):
+        assert np.all(orc.sample_texture_grad(flat, uv, (dx, 0.0), (0.0, dx)) == np.float32(0.3217))
+    ramp = dict(format="rgba8_unorm", levels=scenes.mip_chain(np.tile(np.arange(0, 256, 32, dtype=np.uint8)[None, :, None], (8, 1, 4))))
+    coarse = orc.sample_texture_grad(ramp, (0.5, 0.5), (4.0, 0.0), (0.0, 4.0))
+    assert np.allclose(coarse, ramp["levels"][-1][0, 0] / 255.0)
+    assert abs(orc.sample_texture_grad(ramp, (0.5, 0.5), (1e-4, 0.0), (0.0, 1e-4))[0] - (96 + 128) / 2 / 255.0) < 1e-6
+    assert orc.lib().orc_srgb8_to_linear.restype is not None
+
+
 def test_screenshot_encoders_round_trip(lib, tmp_path):
     """screenshot.c: PNG (stored deflate, CRCs, Adler-32) and run-length Radiance files decode to what was stored; the two
     half-bit frames combine to the fp16 image (main.c:2339-2350); the oracle's copy pass supplies the frames."""

@@ -128,3 +128,29 @@ def test_frames_every_variant(fr, name):
         return
     assert rays == int(fr[f"{name}.rays"])
     assert np.array_equal(_bits(accum), _bits(fr[f"{name}.accum"])), f"{name}: image differs from the compiled reference shader"
+
+
+def test_textured_frame(fr):
+    """Mip-mapped material textures: the oracle's derivative block (shading_pass.frag.glsl:604-627) and its use of the three
+    textureGrad fetches against the compiled reference GLSL, which called the same sampler (the sampler itself is the oracle's
+    definition: texture filtering is driver code). Geometry and lights are those of scene_v3."""
+    from risltc_b200 import scenes
+    W, H, size = 64, 36, 32
+    scene = scenes.many_light_room(12, 10, seed=3, width=W, height=H)
+    textures, cursor = [], 0
+    names = {v: k for k, v in orc.TEXEL.items()}
+    for fmt, count in zip(fr["scene_tex.formats"], fr["scene_tex.level_counts"]):
+        levels = []
+        for l in range(int(count)):
+            n = max(1, size >> l)
+            levels.append(fr["scene_tex.texels"][cursor:cursor + n * n * 4].reshape(n, n, 4)); cursor += n * n * 4
+        textures.append(dict(format=names[int(fmt)], levels=levels))
+    scene["textures"] = textures
+    osc = orc.OracleScene(scene, fr["ltc.rgba16"], fr["ltc.rg16"])
+    cs = [orc.Constants.from_buffer_copy(bytes(b)) for b in fr["scene_tex.constants"]]
+    accum, vis, rays = osc.render(cs, orc.variant())
+    assert rays == int(fr["scene_tex.rays"])
+    assert np.array_equal(_bits(accum), _bits(fr["scene_tex.accum"]))
+    # and the textures matter: the flat-material frame of the same scene differs
+    flat = np.asarray(fr["ris_ltc_v3.accum"])
+    assert np.mean(np.any(accum != flat, axis=-1)) > 0.5

@@ -15,7 +15,10 @@ def image_metrics(a, b):
 def setup_device(dev, scene, rgba, rg, var, width, height, records, stripes=(8, 0, 1)):
     from risltc_b200.scenes import material_constants
     dev.upload_mesh(scene["mesh"])
-    dev.upload_materials(material_constants(scene["materials"]))
+    if scene.get("textures") is not None:
+        dev.upload_textures(scene["textures"])
+    else:
+        dev.upload_materials(material_constants(scene["materials"]))
     dev.upload_lights(records)
     dev.upload_ltc(rgba, rg)
     dev.set_variant(var)

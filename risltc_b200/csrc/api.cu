@@ -117,8 +117,10 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaEventCreateWithFlags(&d->ev_resolved[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_resolved[1], cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
 	for (auto& ev : d->ev) CU(cudaEventCreate(&ev));
-	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
-	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	d->sm_count = prop.multiProcessorCount;
 	CU(cudaMalloc(&d->px.counters, 8 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 8 * sizeof(unsigned long long)));
@@ -147,7 +149,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 static void free_second_set(risltc_device_t* d) {
 	if (d->stream2) cudaStreamSynchronize(d->stream2);
 	cudaFree(d->px2.visibility); cudaFree(d->px2.origin); cudaFree(d->px2.base); cudaFree(d->px2.group); cudaFree(d->px2.ray_a); cudaFree(d->px2.ray_b);
-	cudaFree(d->px2.pick); cudaFree(d->px2.ticket); cudaFree(d->raster2.zbuf); cudaFree(d->raster2.items); cudaFree(d->raster2.counter);
+	cudaFree(d->px2.pick); cudaFree(d->px2.shade); cudaFree(d->px2.ticket); cudaFree(d->raster2.zbuf); cudaFree(d->raster2.items); cudaFree(d->raster2.counter);
 	d->px2 = PixelBuffers(); d->raster2 = RasterBuffers();
 	d->set2_ready = false; d->last_set = 0;
 }
@@ -155,6 +157,7 @@ static void free_second_set(risltc_device_t* d) {
 static void free_targets(risltc_device_t* d) {
 	free_second_set(d);
 	cudaFree(d->px.pick); d->px.pick = nullptr;
+	cudaFree(d->px.shade); d->px.shade = nullptr;
 	cudaFree(d->px.visibility); cudaFree(d->px.origin); cudaFree(d->px.base); cudaFree(d->px.group);
 	cudaFree(d->px.ray_a); cudaFree(d->px.ray_b); cudaFree(d->own_accum); cudaFree(d->raster.zbuf); d->raster.zbuf = nullptr;
 	d->px.visibility = nullptr; d->px.origin = d->px.base = d->px.group = d->px.ray_a = d->px.ray_b = nullptr;
@@ -397,6 +400,7 @@ static int ensure_second_set(risltc_device_t* d) {
 	CU(cudaMalloc(&p.origin, pixels * sizeof(float4)));
 	CU(cudaMalloc(&p.base, pixels * sizeof(float4)));
 	CU(cudaMalloc(&p.pick, pixels * sizeof(uint4)));
+	CU(cudaMalloc(&p.shade, 6 * pixels * sizeof(float4)));
 	CU(cudaMalloc(&p.group, pixels * d->group_slots * sizeof(float4)));
 	CU(cudaMalloc(&p.ray_a, pixels * d->ray_slots * sizeof(float4)));
 	CU(cudaMalloc(&p.ray_b, pixels * d->ray_slots * sizeof(float4)));
@@ -470,6 +474,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMalloc(&d->px.origin, pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->px.base, pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->px.pick, pixels * sizeof(uint4)));
+	CU(cudaMalloc(&d->px.shade, 6 * pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->raster.zbuf, pixels * sizeof(unsigned long long)));
 	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
@@ -532,8 +537,11 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		const uint32_t tiles_x = (d->width + 7) / 8, tile_count = tiles_x * ((d->stripes.owned_rows + 3) / 4);
 		uint32_t ctas = (uint32_t) d->sm_count;
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
-		if (smem) ris_ltc3_kernel<true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-		else ris_ltc3_kernel<false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		const bool textured = d->view.textures != nullptr;
+		if (smem && !textured) ris_ltc3_kernel<true, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		else if (!textured) ris_ltc3_kernel<false, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		else if (smem) ris_ltc3_kernel<true, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		else ris_ltc3_kernel<false, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		CU(cudaEventRecord(between, stream));
 		{
 			// phase-synchronous CTAs (shade_fast.cuh), two resident per SM, each walking over 8x4-pixel tiles

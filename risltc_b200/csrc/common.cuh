@@ -103,6 +103,8 @@ struct PixelBuffers {
 	float4* ray_a;          // [L*S*2][pixels] {dir xyz, t_max}
 	float4* ray_b;          // [L*S*2][pixels] {term rgb, valid}
 	uint4* pick;            // [pixels] RIS winner of the specialised path: light index, W (float bits), RNG state, unused
+	float4* shade;          // [6][pixels] shading point and LTC coefficients of the specialised path, written by the RIS kernel for the
+	                        // winner kernel: {position, roughness} {normal, d0} {diffuse albedo, d1} {F0, d2} {outgoing, d3} {d4, d5, -, -}
 	float4* accum;          // [pixels] RGBA32F running mean
 	unsigned long long* counters;   // [0] shaded pixels, [1] rays traced, [3] candidates; [4..7] rays, node visits, triangle tests, occluded rays of the counting shadow-ray kernel
 	unsigned int* ticket;           // [0] next unclaimed ray of the trace kernel, [1] next tile of ris_ltc3_kernel, [2] of winner_kernel (zero between frames)

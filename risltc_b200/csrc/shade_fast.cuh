@@ -148,7 +148,7 @@ __device__ __forceinline__ void drain(const float* queue, float* ff, uint32_t fi
 	__syncwarp();
 }
 
-template <bool SMEM>
+template <bool SMEM, bool TEXTURED>
 __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
 	extern __shared__ float4 sm_base[];
 	const int N = (int) s.light_count;
@@ -189,10 +189,18 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 		uint32_t seed = 0;
 		if (active) {
 			++shaded;
-			sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
+			sp = reconstruct_shading_point<TEXTURED>(s, f, prim, primary_ray(f, x, y));
 			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
 			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
 			seed = noise_seed(x, y, f.width, f.frame_word);
+			// the shading point and the fetched LTC table values for winner_kernel (d1 = -s20 is the table value itself)
+			const size_t n = out.pixel_count;
+			out.shade[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, sp.roughness);
+			out.shade[n + pixel] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, ltc.s00);
+			out.shade[2 * n + pixel] = make_float4(sp.diffuse_albedo.x, sp.diffuse_albedo.y, sp.diffuse_albedo.z, -ltc.s20);
+			out.shade[3 * n + pixel] = make_float4(sp.fresnel_0.x, sp.fresnel_0.y, sp.fresnel_0.z, ltc.s11);
+			out.shade[4 * n + pixel] = make_float4(sp.outgoing.x, sp.outgoing.y, sp.outgoing.z, ltc.s02);
+			out.shade[5 * n + pixel] = make_float4(ltc.s22, ltc.albedo, 0.0f, 0.0f);
 		}
 		// ---- RIS over 32 candidates, RL_CHUNK at a time
 		float w_sum = 0.0f, chosen_p_hat = 0.0f;
@@ -335,11 +343,23 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 		TechniqueTerms t;
 		t.flip = false; t.specular_total = 0.0f;
 		const float4* light_record = s.lights + (size_t) (live ? pick.x : 0u) * s.light_stride4;
-		if (shaded) sp = reconstruct_shading_point(s, f, prim, primary_ray(f, x, y));
-		if (live) {
-			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
-			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
-			t.flip = plane_side(sp.position, __ldg(light_record + 1)) < 0.0f;
+		if (shaded) {
+			// the shading point and the LTC table values as ris_ltc3_kernel computed them (G-buffer decode, texture fetches, acos
+			// and the table lookup are not repeated here); everything derived from them is recomputed with the same operations
+			const size_t n = out.pixel_count;
+			const float4 q0 = out.shade[pixel], q1 = out.shade[n + pixel], q2 = out.shade[2 * n + pixel], q3 = out.shade[3 * n + pixel];
+			const float4 q4 = out.shade[4 * n + pixel], q5 = out.shade[5 * n + pixel];
+			sp.position = mk3(q0.x, q0.y, q0.z); sp.roughness = q0.w;
+			sp.normal = mk3(q1.x, q1.y, q1.z);
+			sp.diffuse_albedo = mk3(q2.x, q2.y, q2.z);
+			sp.fresnel_0 = mk3(q3.x, q3.y, q3.z);
+			sp.outgoing = mk3(q4.x, q4.y, q4.z);
+			sp.lambert_outgoing = dot3(sp.normal, sp.outgoing);
+			if (live) {
+				const float d[6] = { q1.w, q2.w, q3.w, q4.w, q5.x, q5.y };
+				ltc = ltc_frame_from_fetch(d, sp.position, sp.normal, sp.outgoing);
+				t.flip = plane_side(sp.position, __ldg(light_record + 1)) < 0.0f;
+			}
 		}
 		uint32_t seed = pick.z;
 		float3 dir0 = mk3(0.0f, 0.0f, 0.0f), dir1 = dir0;

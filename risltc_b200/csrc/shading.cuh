@@ -126,6 +126,9 @@ struct ShadingPoint {  // shading_data_t, brdfs.glsl:22-39
 
 // get_shading_data, shading_pass.frag.glsl:571-672. Scenes with flat materials (no texture objects) skip the screen-space
 // derivative block (:604-627), which only feeds the three textureGrad fetches (:629-633).
+// TEXTURED = false compiles the texture path out (the production RIS kernel has one instantiation per case, so that scenes
+// with flat materials carry none of the sampler's code or registers).
+template <bool TEXTURED = true>
 __device__ ShadingPoint reconstruct_shading_point(const SceneView& s, const FrameUniforms& f, uint32_t prim, float3 ray_dir) {
 	ShadingPoint r;
 	float3 p[3], n[3]; float2 uv[3];
@@ -148,7 +151,7 @@ __device__ ShadingPoint reconstruct_shading_point(const SceneView& s, const Fram
 	float3 ng = normalize3(mk3(fmaf(bx, n[0].x, fmaf(by, n[1].x, bz * n[2].x)), fmaf(bx, n[0].y, fmaf(by, n[1].y, bz * n[2].y)), fmaf(bx, n[0].z, fmaf(by, n[1].z, bz * n[2].z))));
 	uint32_t mat = __ldg(&s.material_indices[prim]);
 	float4 m0, m1;   // {base colour rgb, -}, {linear roughness, metalicity, normal.r, normal.g}
-	if (s.textures) {
+	if (TEXTURED && s.textures) {
 		const float3 to0_ = sub3(origin, p[0]);
 		const float det_0_dir_edge_1 = dot3(to0_, ray_cross_e1);
 		const float3 edge_0_cross_0 = cross3(e0, to0_);
@@ -269,6 +272,30 @@ __device__ LtcFrame make_ltc_frame(const SceneView& s, float fresnel_0, float ro
 	          (-normal.x) * pos.x + (-normal.y) * pos.y + (-normal.z) * pos.z);
 	// shading_to_cosine * world_to_shading, element (row i, column j) = S[i][0] W[0][j] + S[i][1] W[1][j] + S[i][2] W[2][j];
 	// the structurally-zero products add exact zeros, so only the non-zero ones are written.
+	l.qx = mk3(l.s00 * x_axis.x + l.s02 * normal.x, l.s00 * x_axis.y + l.s02 * normal.y, l.s00 * x_axis.z + l.s02 * normal.z);
+	l.qy = mk3(l.s11 * y_axis.x, l.s11 * y_axis.y, l.s11 * y_axis.z);
+	l.qz = mk3(l.s20 * x_axis.x + l.s22 * normal.x, l.s20 * x_axis.y + l.s22 * normal.y, l.s20 * x_axis.z + l.s22 * normal.z);
+	l.qt = mk3(l.s00 * l.t.x + l.s02 * l.t.z, l.s11 * l.t.y, l.s20 * l.t.x + l.s22 * l.t.z);
+	return l;
+}
+
+// The same frame from the six fetched table values (d) and the shading point, for a kernel that receives them from another
+// kernel instead of repeating acos + the bilinear fetch: the identical operations in the identical order.
+__device__ LtcFrame ltc_frame_from_fetch(const float d[6], float3 pos, float3 normal, float3 outgoing) {
+	LtcFrame l;
+	const float n_dot_o = dot3(normal, outgoing);
+	l.s00 = d[0]; l.s20 = -d[1]; l.s11 = d[2]; l.s02 = d[3]; l.s22 = d[4];
+	l.albedo = d[5];
+	const float det2 = d[0] * d[4] + d[1] * d[3];
+	l.det = d[2] * det2;
+	const float inv2 = 1.0f / det2;
+	l.c00 = d[4] * inv2; l.c20 = d[1] * inv2; l.c11 = 1.0f / d[2]; l.c02 = -d[3] * inv2; l.c22 = d[0] * inv2;
+	const float3 x_axis = normalize3(mk3(fmaf(-n_dot_o, normal.x, outgoing.x), fmaf(-n_dot_o, normal.y, outgoing.y), fmaf(-n_dot_o, normal.z, outgoing.z)));
+	const float3 y_axis = cross3(normal, x_axis);
+	l.rx = x_axis; l.ry = y_axis; l.rz = normal;
+	l.t = mk3((-x_axis.x) * pos.x + (-x_axis.y) * pos.y + (-x_axis.z) * pos.z,
+	          (-y_axis.x) * pos.x + (-y_axis.y) * pos.y + (-y_axis.z) * pos.z,
+	          (-normal.x) * pos.x + (-normal.y) * pos.y + (-normal.z) * pos.z);
 	l.qx = mk3(l.s00 * x_axis.x + l.s02 * normal.x, l.s00 * x_axis.y + l.s02 * normal.y, l.s00 * x_axis.z + l.s02 * normal.z);
 	l.qy = mk3(l.s11 * y_axis.x, l.s11 * y_axis.y, l.s11 * y_axis.z);
 	l.qz = mk3(l.s20 * x_axis.x + l.s22 * normal.x, l.s20 * x_axis.y + l.s22 * normal.y, l.s20 * x_axis.z + l.s22 * normal.z);

@@ -129,6 +129,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	// rasteriser: item queue, {counter, ticket} in one 16-byte block
 	CU(cudaMalloc(&d->raster.items, (size_t) RL_RASTER_MAX_ITEMS * sizeof(RasterItem)));
 	CU(cudaMalloc(&d->raster.counter, 16));
+	CU(cudaMemset(d->raster.counter, 0, 16));
 	d->raster.ticket = (unsigned int*) (d->raster.counter + 1);
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
@@ -408,8 +409,10 @@ static int ensure_second_set(risltc_device_t* d) {
 	CU(cudaMemset(p.ray_b, 0, pixels * d->ray_slots * sizeof(float4)));
 	CU(cudaMemset(p.ticket, 0, 4 * sizeof(unsigned int)));
 	CU(cudaMalloc(&d->raster2.zbuf, pixels * sizeof(unsigned long long)));
+	CU(cudaMemset(d->raster2.zbuf, 0xFF, pixels * sizeof(unsigned long long)));   // kept clear by raster_resolve_kernel from here on
 	CU(cudaMalloc(&d->raster2.items, (size_t) RL_RASTER_MAX_ITEMS * sizeof(RasterItem)));
 	CU(cudaMalloc(&d->raster2.counter, 16));
+	CU(cudaMemset(d->raster2.counter, 0, 16));
 	d->raster2.ticket = (unsigned int*) (d->raster2.counter + 1);
 	d->set2_ready = true;
 	return 0;
@@ -476,6 +479,7 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 	CU(cudaMalloc(&d->px.pick, pixels * sizeof(uint4)));
 	CU(cudaMalloc(&d->px.shade, 6 * pixels * sizeof(float4)));
 	CU(cudaMalloc(&d->raster.zbuf, pixels * sizeof(unsigned long long)));
+	CU(cudaMemset(d->raster.zbuf, 0xFF, pixels * sizeof(unsigned long long)));   // kept clear by raster_resolve_kernel from here on
 	CU(cudaMalloc(&d->own_accum, pixels * sizeof(float4)));
 	CU(cudaMemset(d->own_accum, 0, pixels * sizeof(float4)));
 	d->px.accum = d->own_accum;
@@ -613,11 +617,9 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (d->gbuffer_tune < 2) CU(cudaEventRecord(d->tune_ev[2 * d->gbuffer_tune], stream));
 		if (kind == 1) {
 			// (1) every triangle finds its pixels and competes for them with atomicMin on {t, index} (raster.cuh)
-			CU(cudaMemsetAsync(raster.zbuf, 0xFF, (size_t) px.pixel_count * sizeof(unsigned long long), stream));
-			CU(cudaMemsetAsync(raster.counter, 0, 16, stream));
 			raster_setup_kernel<<<(d->view.triangle_count + 127) / 128, 128, 0, stream>>>(d->view, f, d->stripes, raster);
 			raster_tiles_kernel<<<d->sm_count * 8, 128, 0, stream>>>(d->view, f, d->stripes, raster);
-			raster_resolve_kernel<<<(px.pixel_count + 255) / 256, 256, 0, stream>>>(raster.zbuf, px.visibility, px.pixel_count);
+			raster_resolve_kernel<<<(px.pixel_count + 255) / 256, 256, 0, stream>>>(raster.zbuf, px.visibility, px.pixel_count, raster.counter);
 			d->launches += 2;
 		}
 		else gbuffer_kernel<<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);

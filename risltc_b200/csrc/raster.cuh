@@ -262,10 +262,14 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 	}
 }
 
-__global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long long* zbuf, uint32_t* visibility, uint32_t pixel_count) {
+// Keys -> ids; the kernel also leaves the key buffer, the item counter and the unit ticket cleared for the next frame that uses
+// this set of buffers (they are cleared once when they are allocated), so that a frame needs no memset operations.
+__global__ void __launch_bounds__(256) raster_resolve_kernel(unsigned long long* zbuf, uint32_t* visibility, uint32_t pixel_count, unsigned long long* counter_and_ticket) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0u) { counter_and_ticket[0] = 0ull; counter_and_ticket[1] = 0ull; }
 	if (i >= pixel_count) return;
 	const unsigned long long key = zbuf[i];
+	zbuf[i] = ~0ull;
 	const uint32_t low = (uint32_t) key;
 	visibility[i] = (key == ~0ull) ? 0xFFFFFFFFu : ((low >> 1) | (low << 31));
 }

@@ -95,8 +95,9 @@ int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 /* Two of the passes have two implementations each that produce bit-identical buffers (tests/test_gpu_frames.py):
  *   visibility pass (visibility_pass.*.glsl): the triangle-parallel rasteriser or the per-pixel BVH walk; AUTO (default)
  *     times both on the first two frames after upload_scene / resize and keeps the faster;
- *   ray queries (shading_pass.frag.glsl:112-129): the 4-wide tree with 8-bit boxes (default) or the binary tree.
- * This call pins them (the environment variables RISLTC_GBUFFER=raster|bvh and RISLTC_TRACE=4|2 do the same at create).
+ *   ray queries (shading_pass.frag.glsl:112-129): the 4-wide tree with 8-bit boxes, traversed once for the two rays of
+ *     a pixel (PAIRS, default) or once per ray (WIDE), or the binary tree.
+ * This call pins them (the environment variables RISLTC_GBUFFER=raster|bvh and RISLTC_TRACE=8|4|2 do the same at create).
  * The shadow-ray kernel additionally times two settings of its triangle-track threshold on the first two frames after
  * upload_scene and keeps the faster (RISLTC_TRI_VOTE=<n> pins it); results do not depend on it either. */
 #define RISLTC_GBUFFER_BVH 0u
@@ -104,6 +105,7 @@ int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 #define RISLTC_GBUFFER_AUTO 2u
 #define RISLTC_SHADOW_BINARY 2u
 #define RISLTC_SHADOW_WIDE 4u
+#define RISLTC_SHADOW_PAIRS 8u
 int risltc_cuda_set_kernels(risltc_device_t* device, uint32_t gbuffer, uint32_t shadow);
 
 /* Frame overlap inside render_frames: consecutive frames alternate between two streams and two sets of per-frame buffers
@@ -185,8 +187,9 @@ int risltc_cuda_kat_noise(risltc_device_t* device, uint32_t width, uint32_t heig
 int risltc_cuda_kat_ltc_coefficients(risltc_device_t* device, const float* inputs /* count x 11: fresnel, roughness, pos, normal, outgoing */,
 	const float ltc_constants[6], float* out, uint32_t count);
 int risltc_cuda_kat_any_hit(risltc_device_t* device, const float* rays /* count x 8: o, tmin, d, tmax */, uint32_t* hits, uint32_t count);
-/* The shadow-ray kernels of the frame path on the same ray array (t_min is their fixed 1e-3): kind 4 = 4-wide quantised
- * tree (default of render_frames), kind 2 = binary tree. */
+/* The shadow-ray kernels of the frame path on the same ray array (t_min is their fixed 1e-3): kind 8 = 4-wide quantised
+ * tree traversed once per pair of rays (default of render_frames; ray i and ray i + count / 2 form a pair and must share
+ * their origin, count even), kind 4 = the same tree, one ray per lane, kind 2 = binary tree. */
 int risltc_cuda_kat_trace(risltc_device_t* device, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind);
 /* Exhaustive device-side check of the kernels' hand-written exactly rounded sequences against the IEEE operations they
  * stand for: [0] inversesqrt vs 1 / sqrt over every float of its fast range, [1] unorm16 vs x / 65535 for 0..65535,

@@ -130,8 +130,8 @@ class Device:
     def set_precision(self, mode):
         _check(lib().risltc_cuda_set_precision(self.h, C.c_uint32({"fast": 0, "exact": 1, "hybrid": 2}[mode])))
 
-    def set_kernels(self, gbuffer="auto", shadow="wide"):
-        _check(lib().risltc_cuda_set_kernels(self.h, C.c_uint32({"bvh": 0, "raster": 1, "auto": 2}[gbuffer]), C.c_uint32({"binary": 2, "wide": 4}[shadow])))
+    def set_kernels(self, gbuffer="auto", shadow="pairs"):
+        _check(lib().risltc_cuda_set_kernels(self.h, C.c_uint32({"bvh": 0, "raster": 1, "auto": 2}[gbuffer]), C.c_uint32({"binary": 2, "wide": 4, "pairs": 8}[shadow])))
 
     def set_frame_overlap(self, mode="auto"):
         _check(lib().risltc_cuda_set_frame_overlap(self.h, C.c_uint32({"off": 0, "on": 1, "auto": 2}[mode])))
@@ -249,7 +249,8 @@ class Device:
         return [int(v) for v in out]
 
     def kat_trace(self, rays, kind=4):
-        """The frame path's shadow-ray kernel (4: 4-wide quantised tree, 2: binary tree) on an array of rays."""
+        """The frame path's shadow-ray kernels on an array of rays (8: 4-wide quantised tree, rays i and i + n / 2 as a pair
+        with a common origin; 4: the same tree, one ray per lane; 2: binary tree)."""
         r = np.ascontiguousarray(rays, dtype=np.float32)
         hits = np.empty(r.shape[0], dtype=np.uint32)
         _check(lib().risltc_cuda_kat_trace(self.h, _p(r), _p(hits), C.c_uint32(r.shape[0]), C.c_uint32(kind)))

@@ -58,7 +58,7 @@ struct risltc_device_s {
 	cudaEvent_t ev_resolved[2] = { nullptr, nullptr }, ev_fork = nullptr, ev_join = nullptr;
 	uint32_t last_set = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
-	int sm_count = 148, trace_resident = 1, trace4_resident = 1;
+	int sm_count = 148, trace_resident = 1, trace4_resident = 1, trace4p_resident = 1;
 	int trace_ctas_per_sm = 0;   // 0: as many as fit
 	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
 	// (1) has two bit-identical implementations: 1 = triangle-parallel rasteriser (raster.cuh; wins when few triangles cover
@@ -72,7 +72,7 @@ struct risltc_device_s {
 	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel, two CTAs per SM: 384 (80 registers), 320 (96) or 256 (128)
 	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
-	uint32_t trace_kind = 4;      // 4: trace4_kernel (4-wide quantised tree), 2: trace_kernel (binary tree)
+	uint32_t trace_kind = 8;      // 8: trace4p_kernel (4-wide quantised tree, the two rays of a pixel per lane), 4: trace4_kernel (one ray per lane), 2: trace_kernel (binary tree)
 	// lanes that must have a triangle waiting before the shadow-ray kernel runs its triangle track. Few occluded rays (C2: 27 %):
 	// a well filled triangle track (8) wins; mostly occluded rays in a deep tree (C4: 93 %): testing the first triangle at once
 	// (1) ends them ~10 % of their node visits earlier. Unless RISLTC_TRI_VOTE pins it, the first two frames after a scene
@@ -133,6 +133,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	d->raster.ticket = (unsigned int*) (d->raster.counter + 1);
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4p_resident, trace4p_kernel<false>, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) { d->tri_vote = (uint32_t) atoi(e); d->trace_pinned = true; d->trace_tune = 3u; }   // tuning knobs
 	for (auto& ev : d->trace_tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 256 || t == 320) ? (uint32_t) t : 384u; }
@@ -142,7 +143,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
 	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
-	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : 4u;
+	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : (atoi(e) == 4) ? 4u : 8u;
 	*device = d;
 	return 0;
 }
@@ -449,7 +450,7 @@ extern "C" int risltc_cuda_set_precision(risltc_device_t* d, uint32_t mode) {
 
 extern "C" int risltc_cuda_set_kernels(risltc_device_t* d, uint32_t gbuffer, uint32_t shadow) {
 	if (use(d)) return 1;
-	if (gbuffer > RISLTC_GBUFFER_AUTO || (shadow != RISLTC_SHADOW_BINARY && shadow != RISLTC_SHADOW_WIDE)) return fail("set_kernels: unknown kernel", nullptr);
+	if (gbuffer > RISLTC_GBUFFER_AUTO || (shadow != RISLTC_SHADOW_BINARY && shadow != RISLTC_SHADOW_WIDE && shadow != RISLTC_SHADOW_PAIRS)) return fail("set_kernels: unknown kernel", nullptr);
 	CU(cudaStreamSynchronize(d->stream));
 	d->gbuffer_pinned = gbuffer != RISLTC_GBUFFER_AUTO;
 	d->gbuffer_kind = (gbuffer == RISLTC_GBUFFER_BVH) ? 0u : 1u;
@@ -631,7 +632,8 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (traced) {
 			// (3) persistent any-hit traversal over all ray slots
 			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < d->trace4_resident) ? d->trace_ctas_per_sm : d->trace4_resident;
+			const int resident = (d->trace_kind == 8) ? d->trace4p_resident : d->trace4_resident;
+			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < resident) ? d->trace_ctas_per_sm : resident;
 			static const uint32_t vote_candidates[2] = { 8u, 1u };
 			if (d->trace_tune == 2) {
 				float ms[2] = { 0.0f, 0.0f };
@@ -643,7 +645,9 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			}
 			const uint32_t tuning = d->trace_tune;
 			if (tuning < 2) { d->tri_vote = vote_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
-			if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
+			if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill);
+			else if (d->trace_kind == 8) trace4p_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill);
+			else if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
 			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
 			if (tuning < 2) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
@@ -858,8 +862,9 @@ struct DeviceArray {
 };
 #define KAT_GRID(count) ((count) + 127) / 128, 128
 
-// The production shadow-ray kernels (kind 4: trace4_kernel, 2: trace_kernel) on an array of rays with t_min = 1e-3:
-// the rays are laid out as one ray slot of `count` pixels, exactly what the shading kernels leave behind.
+// The production shadow-ray kernels (kind 8: trace4p_kernel, 4: trace4_kernel, 2: trace_kernel) on an array of rays with
+// t_min = 1e-3: the rays are laid out as one ray slot of `count` pixels, exactly what the shading kernels leave behind; for
+// kind 8 as two ray slots of count / 2 pixels (ray i and ray i + count / 2 must share their origin, count must be even).
 __global__ void kat_trace_fill_kernel(const float* rays, float4* origin, float4* ray_a, float4* ray_b, uint32_t count) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= count) return;
@@ -875,15 +880,17 @@ __global__ void kat_trace_read_kernel(const float4* ray_b, uint32_t* hits, uint3
 extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint32_t* hits, uint32_t count, uint32_t kind) {
 	if (use(d)) return 1;
 	if (!d->nodes || !d->nodes4) return fail("kat_trace: upload_scene first", nullptr);
-	if (kind != 2 && kind != 4) return fail("kat_trace: kind must be 2 or 4", nullptr);
+	if (kind != 2 && kind != 4 && kind != 8) return fail("kat_trace: kind must be 2, 4 or 8", nullptr);
+	if (kind == 8 && (count & 1u)) return fail("kat_trace: kind 8 takes an even number of rays (two slots of count / 2 pixels)", nullptr);
 	DeviceArray<float> r; DeviceArray<uint32_t> h; DeviceArray<float4> og, ra, rb; DeviceArray<unsigned int> ticket;
 	if (r.init(rays, (size_t) count * 8) || h.init(nullptr, count) || og.init(nullptr, count) || ra.init(nullptr, count) || rb.init(nullptr, count) || ticket.init(nullptr, 4))
 		return fail("kat_trace: allocation failed", nullptr);
 	CU(cudaMemset(ticket.p, 0, 4 * sizeof(unsigned int)));
 	PixelBuffers px = {};
-	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = count;
+	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = (kind == 8) ? count / 2u : count;
 	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
-	if (kind == 4) trace4_kernel<false><<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
+	if (kind == 8) trace4p_kernel<false><<<d->sm_count * d->trace4p_resident, 128>>>(d->view, px, count / 2u, d->tri_vote, d->refill);
+	else if (kind == 4) trace4_kernel<false><<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
 	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
 	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
 	CU(cudaDeviceSynchronize());

@@ -203,7 +203,7 @@ def test_kernel_alternatives_are_bit_identical(device, ltc_tables):
     try:
         for stripes in ((8, 0, 1), (8, 1, 3)):
             results = []
-            for gbuffer, shadow in (("raster", "wide"), ("bvh", "wide"), ("raster", "binary"), ("auto", "wide")):
+            for gbuffer, shadow in (("raster", "wide"), ("bvh", "wide"), ("raster", "binary"), ("auto", "wide"), ("raster", "pairs"), ("auto", "pairs")):
                 setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records, stripes)
                 device.set_kernels(gbuffer, shadow)
                 device.render_frames(cs)
@@ -225,7 +225,7 @@ def test_kernel_alternatives_are_bit_identical(device, ltc_tables):
         assert np.array_equal(images[0][0], images[1][0])
         assert np.array_equal(images[0][1].view(np.uint32), images[1][1].view(np.uint32))
     finally:
-        device.set_kernels("auto", "wide")
+        device.set_kernels("auto", "pairs")
         device.set_frame_overlap("auto")
         device.resize(W, H, 8, 0, 1)
 

@@ -122,6 +122,24 @@ def test_any_hit_matches_oracle_bit_for_bit(device, ltc_tables):
         got = device.kat_trace(rays, kind)
         assert np.array_equal(got, want), f"trace kernel {kind}: {np.count_nonzero(got != want)} of {n} any-hit decisions differ"
     assert 0.05 < want.mean() < 0.98
+    # the default kernel traverses the tree once for the two rays of a pixel (ray i and ray i + n / 2 share their origin):
+    # nearly parallel pairs (two samples of one small light), unrelated pairs (other octants: traced alone), pairs of which
+    # one ray is switched off (t_max below t_min), pairs that repeat the vertex / edge rays above
+    half = n // 2
+    pairs = rays.copy()
+    pairs[half:, 0:3] = pairs[:half, 0:3]
+    jitter = pairs[:half, 4:7] + rng.normal(scale=0.03, size=(half, 3)).astype(np.float32)
+    coherent = rng.random(half) < 0.6
+    pairs[half:, 4:7][coherent] = (jitter / np.linalg.norm(jitter, axis=1, keepdims=True))[coherent]
+    pairs[half:half + 1000, 4:7] = pairs[:1000, 4:7]                       # the exact vertex / edge rays, twice in a pair
+    pairs[half:half + 1000, 7] = rng.uniform(0.5, 25.0, 1000)
+    off = rng.random(n) < 0.1
+    pairs[off, 7] = 0.0
+    want2 = np.array([osc.any_hit(r[0:3], r[4:7], float(r[3]), float(r[7])) if r[7] > 1e-3 else 0 for r in pairs], dtype=np.uint32)
+    for kind in (8, 4):
+        got = device.kat_trace(pairs, kind)
+        assert np.array_equal(got, want2), f"trace kernel {kind} on pairs: {np.count_nonzero(got != want2)} of {n} any-hit decisions differ"
+    assert 0.05 < want2.mean() < 0.98
 
 
 def test_exactly_rounded_sequences_exhaustively(device):

@@ -338,6 +338,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
     e2e_value = samples_per_step * args.steps / float(e2e_t[0]) / 1e9
     light_bytes = len(app.write_lights())
     triangles = int(wl["scene"]["mesh"]["material_indices"].shape[0])
+    bvh = dev.bvh_stats()
 
     # ---- tear down in dependency order before anything else is created. torch's allocators record an event on every stream
     # a block was used on when the block is freed, and the stream here belongs to the library's device object: the tensors
@@ -379,7 +380,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
         bytes_per_ray = (nodes * NODE_BYTES + tris * TRIANGLE_BYTES) / rays + RAY_RECORD_BYTES if rays else None
         hbm_peak = peaks.get("hbm_gbs", 6650.0) * world
         trace_gbs = bytes_per_ray * rays / trace_s / 1e9 if rays and trace_s > 0 else None
-        roofline_trace = dict(kernel="trace4_kernel (3: any-hit traversal of the 4-wide, 8-bit BVH)", bound="latency / ALU pipe (the working set of nodes and triangles is L1/L2-resident; HBM only streams the ray records)",
+        roofline_trace = dict(kernel="trace4p_kernel (3: any-hit traversal of the 4-wide, 8-bit BVH, one traversal per pair of rays of a pixel; node visits and triangle tests are counted per traversal)", bound="latency / ALU pipe (the working set of nodes and triangles is L1/L2-resident; HBM only streams the ray records)",
                               rays_per_step=rays, grays_per_s=rays / trace_s / 1e9 if trace_s > 0 else None, ms_per_launch=per_step["trace_ms"] / spp,
                               node_visits_per_ray=nodes / rays if rays else None, triangle_tests_per_ray=tris / rays if rays else None,
                               occluded_fraction=occluded / rays if rays else None, bytes_per_ray=bytes_per_ray,
@@ -394,6 +395,9 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
                     ms_per_step=ms_max / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=wl["desc"], variant="light_reservoir (m=32) + sample_polygon_ltc_cp + mis_optimal_clamped, S=1, L=1" if wl["name"] != "c1" else "light_uniform + projected_solid_angle",
                                 lights=wl["lights"], triangles=triangles, width=W, height=H, spp=spp,
+                                acceleration_structure=dict(builder=bvh["builder"], build_ms=round(bvh["build_ms"], 1), device_ms=[round(x, 2) for x in bvh["device_ms"]],
+                                                            wide_nodes=bvh["wide_nodes"], depth=[bvh["binary_depth"], bvh["wide_depth"]],
+                                                            note="built once at upload_scene, outside the timed region (scene.c:142-406 builds once per scene, too)"),
                                 precision=args.precision, parallelism=f"image stripes of {args.stripe_height} rows x{world}, scene replicated, one gather per step",
                                 l2=f"L2 flushed (192 MiB fill) before the timed region; every frame streams {per_device_mb:.0f} MB of per-pixel buffers per device through a 126 MB L2"
                                    + (" (larger than L2)" if per_device_mb * 2 ** 20 > L2_BYTES else " (smaller than L2: frames of a step reuse it, as they do in production)")),

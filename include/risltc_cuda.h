@@ -92,6 +92,18 @@ int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* var
 #define RISLTC_PRECISION_EXACT 1u
 int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 
+/* Builder of the acceleration structures (create_acceleration_structure, scene.c:142-406, where the driver builds on the
+ * device): HOST = binned SAH on one host thread (best traversal cost, ~1.3 us per triangle), DEVICE = Morton-order radix tree
+ * built by kernels (bvh_gpu.cu; 5 M triangles in 15 ms instead of 6.9 s, shadow rays 1.2-1.5x costlier), AUTO (default) =
+ * DEVICE from 8 M triangles on. Takes effect at the next upload_scene; images do not depend on it. Environment: RISLTC_BVH_BUILD=host|gpu.
+ * bvh_stats: {builder used, wall ms of the build, device ms of sort + hierarchy / boxes + records / 4-wide collapse,
+ * binary node slots, 4-wide nodes, binary depth << 16 | 4-wide depth}. */
+#define RISLTC_BVH_BUILDER_HOST 0u
+#define RISLTC_BVH_BUILDER_DEVICE 1u
+#define RISLTC_BVH_BUILDER_AUTO 2u
+int risltc_cuda_set_bvh_builder(risltc_device_t* device, uint32_t builder);
+int risltc_cuda_bvh_stats(risltc_device_t* device, double stats[8]);
+
 /* Two of the passes have two implementations each that produce bit-identical buffers (tests/test_gpu_frames.py):
  *   visibility pass (visibility_pass.*.glsl): the triangle-parallel rasteriser or the per-pixel BVH walk; AUTO (default)
  *     times both on the first two frames after upload_scene / resize and keeps the faster;
@@ -200,6 +212,9 @@ int risltc_cuda_kat_exact_math(risltc_device_t* device, uint64_t mismatches[3]);
  * violations of the 4-wide tree (a leaf / node not referenced exactly once, a quantised box that does not contain the
  * binary tree's box), binary nodes, 4-wide nodes, depth << 32 | children per 4-wide node x 100}. The first three must be 0. */
 int risltc_cuda_check_bvh(const float* vertices, uint64_t triangle_count, uint32_t max_leaf, uint64_t report[6]);
+/* The same report for the acceleration structures upload_scene left on the device, whichever builder made them; report[0]
+ * additionally counts triangle records that are not bit-identical to {v0, v1 - v0, v2 - v0, id} of their triangle. */
+int risltc_cuda_check_scene_bvh(risltc_device_t* device, uint64_t report[6]);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,24 @@ class Device:
     def set_kernels(self, gbuffer="auto", shadow="pairs"):
         _check(lib().risltc_cuda_set_kernels(self.h, C.c_uint32({"bvh": 0, "raster": 1, "auto": 2}[gbuffer]), C.c_uint32({"binary": 2, "wide": 4, "pairs": 8}[shadow])))
 
+    def set_bvh_builder(self, builder="auto"):
+        """Builder of the acceleration structures for the next upload_mesh: host (binned SAH), device (Morton-order radix tree) or auto."""
+        _check(lib().risltc_cuda_set_bvh_builder(self.h, C.c_uint32({"host": 0, "device": 1, "auto": 2}[builder])))
+
+    def bvh_stats(self):
+        out = (C.c_double * 8)()
+        _check(lib().risltc_cuda_bvh_stats(self.h, out))
+        v = [float(x) for x in out]
+        return dict(builder="device" if v[0] else "host", build_ms=v[1], device_ms=v[2:5], binary_node_slots=int(v[5]), wide_nodes=int(v[6]),
+                    binary_depth=int(v[7]) >> 16, wide_depth=int(v[7]) & 0xFFFF)
+
+    def check_scene_bvh(self):
+        """Invariants of the acceleration structures on the device (see check_bvh); the first three must be 0."""
+        report = (C.c_uint64 * 6)()
+        _check(lib().risltc_cuda_check_scene_bvh(self.h, report))
+        r = [int(x) for x in report]
+        return dict(bad_order=r[0], bad_binary=r[1], bad_wide=r[2], binary_nodes=r[3], wide_nodes=r[4], depth=r[5] >> 32, children_per_node=(r[5] & 0xFFFFFFFF) / 100.0)
+
     def set_frame_overlap(self, mode="auto"):
         _check(lib().risltc_cuda_set_frame_overlap(self.h, C.c_uint32({"off": 0, "on": 1, "auto": 2}[mode])))
 

@@ -35,7 +35,7 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    units = [(CSRC / "api.cu", NVCC_EXACT), (CSRC / "generic.cu", NVCC_EXACT), (CSRC / "kat.cu", NVCC_EXACT), (CSRC / "winner_cr.cu", NVCC_EXACT), (CSRC / "bvh_build.cpp", [])]
+    units = [(CSRC / "api.cu", NVCC_EXACT), (CSRC / "generic.cu", NVCC_EXACT), (CSRC / "kat.cu", NVCC_EXACT), (CSRC / "winner_cr.cu", NVCC_EXACT), (CSRC / "bvh_gpu.cu", NVCC_EXACT), (CSRC / "bvh_build.cpp", [])]
     deps = [u for u, _ in units] + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc")) + [PKG.parent / "include" / "risltc_cuda.h"]
     if force or _stale(CUDA_LIB, deps):
         env = {**os.environ, "CC": "gcc", "CXX": "g++"}

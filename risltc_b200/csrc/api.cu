@@ -15,6 +15,7 @@
 #include <vector>
 #include <algorithm>
 #include <utility>
+#include <chrono>
 
 using namespace exact;
 
@@ -28,6 +29,11 @@ int rl_fail(const char* what, const char* detail) {
 #define fail rl_fail
 
 #define RL_FRAME_EVENTS 6
+// auto: scenes from 8 M triangles on are built on the device. Measured on B200 (gpurun_out/wl_*_bvh_*.json, round 2): 5 M triangles
+// (C4) build in 6.9 s on the host and in 14.5 ms on the device (4.1 ms of kernels), but the Morton-order tree costs +23 % shadow-ray
+// time and +33 % primary-visibility time there (+50 % shadow-ray time on the small scenes C2 / C3): a scene is built once and
+// rendered for thousands of frames, so the host's binned-SAH tree stays the default until its build time reaches ~10 s.
+#define RL_GPU_BUILD_TRIANGLES (1ull << 23)
 
 struct risltc_device_s {
 	int ordinal = 0;
@@ -81,6 +87,11 @@ struct risltc_device_s {
 	uint32_t trace_tune = 0;      // 0, 1: time candidate 0 / 1 next, 2: both in flight, 3: decided
 	bool trace_pinned = false;
 	cudaEvent_t trace_tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	// acceleration-structure builder: 0 = host (binned SAH, bvh_build.cpp), 1 = device (Morton-order radix tree, bvh_gpu.cu), 2 = auto:
+	// the device builder from RL_GPU_BUILD_TRIANGLES triangles on, where the host build takes ~10 s (RISLTC_BVH_BUILD=host|gpu)
+	uint32_t bvh_builder = 2;
+	double bvh_stats[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };   // builder used, wall ms of the build, device ms x3, binary node slots, 4-wide nodes, binary depth << 16 | 4-wide depth
+	uint64_t node_count = 0, node4_count = 0;
 	unsigned long long launches = 0;
 	bool timed = false;
 	// per-frame events of the last batch: RL_FRAME_EVENTS per frame (before (1), after (1), after (2a), after (2b) = after (2), after (3), after (4))
@@ -143,6 +154,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
 	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
+	if (const char* e = getenv("RISLTC_BVH_BUILD")) d->bvh_builder = (strcmp(e, "gpu") == 0 || strcmp(e, "device") == 0) ? 1u : (strcmp(e, "host") == 0) ? 0u : 2u;
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : (atoi(e) == 4) ? 4u : 8u;
 	*device = d;
 	return 0;
@@ -207,44 +219,63 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	CU(cudaMemcpy(d->normals_uv, normals_and_tex_coords, T * 3 * sizeof(ushort4), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(d->material_indices, material_indices, T, cudaMemcpyHostToDevice));
 	// acceleration structure
-	std::vector<float> verts;
-	dequantize_mesh_for_bvh(quantized_positions, T, factor, summand, verts);
-	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
 	uint32_t max_leaf = 2;   // measured best for the 4-wide any-hit kernel (a triangle test costs about as much as three box tests)
 	if (const char* e = getenv("RISLTC_BVH_LEAF")) max_leaf = (uint32_t) atoi(e);
-	build_bvh(verts.data(), T, nodes, order, max_leaf);
-	// gbuffer_kernel, the exact-precision paths and trace_kernel walk the binary tree with RL_STACK entries per thread
-	if (bvh_depth(nodes) > RL_STACK) return fail("upload_scene: the binary acceleration structure is deeper than the traversal stack", nullptr);
-	std::vector<BvhNode> dn(nodes.size());
-	for (size_t i = 0; i != nodes.size(); ++i) {
-		const BvhNodeHost& n = nodes[i];
-		dn[i].a = make_float4(n.left_lo[0], n.left_lo[1], n.left_lo[2], n.left_hi[0]);
-		dn[i].b = make_float4(n.left_hi[1], n.left_hi[2], n.right_lo[0], n.right_lo[1]);
-		dn[i].c = make_float4(n.right_lo[2], n.right_hi[0], n.right_hi[1], n.right_hi[2]);
-		dn[i].d = make_int4(n.left, n.right, 0, 0);
+	const bool on_device = (d->bvh_builder == 1u || (d->bvh_builder == 2u && T >= RL_GPU_BUILD_TRIANGLES)) && T > 16;
+	const auto wall_start = std::chrono::steady_clock::now();
+	for (double& v : d->bvh_stats) v = 0.0;
+	if (on_device) {
+		uint64_t counts[2]; uint32_t depths[2]; float ms[3];
+		if (rl_build_bvh_gpu(d->positions, T, factor, summand, max_leaf, &d->nodes, &d->tris, &d->nodes4, counts, depths, ms)) return 1;
+		if (depths[0] > RL_STACK) return fail("upload_scene: the device-built binary acceleration structure is deeper than the traversal stack (RISLTC_BVH_BUILD=host builds a balanced one)", nullptr);
+		if (3u * depths[1] + 1u > RL_T4_OVERFLOW) return fail("upload_scene: the device-built acceleration structure is deeper than the traversal stack", nullptr);
+		d->node_count = counts[0]; d->node4_count = counts[1];
+		d->bvh_stats[0] = 1.0; d->bvh_stats[2] = ms[0]; d->bvh_stats[3] = ms[1]; d->bvh_stats[4] = ms[2];
+		d->bvh_stats[7] = (double) ((depths[0] << 16) | depths[1]);
 	}
-	std::vector<BvhTri> dt(T);
-	for (uint64_t slot = 0; slot != T; ++slot) {
-		uint32_t t = order[slot];
-		const float* v = verts.data() + 9 * (size_t) t;
-		uint32_t id = t | ((quantized_positions[6 * (size_t) t + 1] >> 31) << 31);
-		float idf; memcpy(&idf, &id, 4);
-		volatile float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
-		volatile float e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
-		dt[slot].v0 = make_float4(v[0], v[1], v[2], idf);
-		dt[slot].e1 = make_float4(e1x, e1y, e1z, 0.0f);
-		dt[slot].e2 = make_float4(e2x, e2y, e2z, 0.0f);
+	else {
+		std::vector<float> verts;
+		dequantize_mesh_for_bvh(quantized_positions, T, factor, summand, verts);
+		std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
+		build_bvh(verts.data(), T, nodes, order, max_leaf);
+		// gbuffer_kernel, the exact-precision paths and trace_kernel walk the binary tree with RL_STACK entries per thread
+		const uint32_t depth2 = bvh_depth(nodes);
+		if (depth2 > RL_STACK) return fail("upload_scene: the binary acceleration structure is deeper than the traversal stack", nullptr);
+		std::vector<BvhNode> dn(nodes.size());
+		for (size_t i = 0; i != nodes.size(); ++i) {
+			const BvhNodeHost& n = nodes[i];
+			dn[i].a = make_float4(n.left_lo[0], n.left_lo[1], n.left_lo[2], n.left_hi[0]);
+			dn[i].b = make_float4(n.left_hi[1], n.left_hi[2], n.right_lo[0], n.right_lo[1]);
+			dn[i].c = make_float4(n.right_lo[2], n.right_hi[0], n.right_hi[1], n.right_hi[2]);
+			dn[i].d = make_int4(n.left, n.right, 0, 0);
+		}
+		std::vector<BvhTri> dt(T);
+		for (uint64_t slot = 0; slot != T; ++slot) {
+			uint32_t t = order[slot];
+			const float* v = verts.data() + 9 * (size_t) t;
+			uint32_t id = t | ((quantized_positions[6 * (size_t) t + 1] >> 31) << 31);
+			float idf; memcpy(&idf, &id, 4);
+			volatile float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2];
+			volatile float e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+			dt[slot].v0 = make_float4(v[0], v[1], v[2], idf);
+			dt[slot].e1 = make_float4(e1x, e1y, e1z, 0.0f);
+			dt[slot].e2 = make_float4(e2x, e2y, e2z, 0.0f);
+		}
+		std::vector<Qbvh4NodeHost> dn4;
+		const uint32_t depth4 = build_qbvh4(nodes, dn4);
+		if (3u * depth4 + 1u > RL_T4_OVERFLOW) return fail("upload_scene: the acceleration structure is deeper than the traversal stack", nullptr);
+		static_assert(sizeof(Qbvh4NodeHost) == sizeof(Qbvh4Node), "node layouts");
+		CU(cudaMalloc(&d->nodes4, dn4.size() * sizeof(Qbvh4Node)));
+		CU(cudaMemcpy(d->nodes4, dn4.data(), dn4.size() * sizeof(Qbvh4Node), cudaMemcpyHostToDevice));
+		CU(cudaMalloc(&d->nodes, dn.size() * sizeof(BvhNode)));
+		CU(cudaMalloc(&d->tris, dt.size() * sizeof(BvhTri)));
+		CU(cudaMemcpy(d->nodes, dn.data(), dn.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(d->tris, dt.data(), dt.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
+		d->node_count = dn.size(); d->node4_count = dn4.size();
+		d->bvh_stats[7] = (double) ((depth2 << 16) | depth4);
 	}
-	std::vector<Qbvh4NodeHost> dn4;
-	const uint32_t depth4 = build_qbvh4(nodes, dn4);
-	if (3u * depth4 + 1u > RL_T4_OVERFLOW) return fail("upload_scene: the acceleration structure is deeper than the traversal stack", nullptr);
-	static_assert(sizeof(Qbvh4NodeHost) == sizeof(Qbvh4Node), "node layouts");
-	CU(cudaMalloc(&d->nodes4, dn4.size() * sizeof(Qbvh4Node)));
-	CU(cudaMemcpy(d->nodes4, dn4.data(), dn4.size() * sizeof(Qbvh4Node), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&d->nodes, dn.size() * sizeof(BvhNode)));
-	CU(cudaMalloc(&d->tris, dt.size() * sizeof(BvhTri)));
-	CU(cudaMemcpy(d->nodes, dn.data(), dn.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(d->tris, dt.data(), dt.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
+	d->bvh_stats[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_start).count();
+	d->bvh_stats[5] = (double) d->node_count; d->bvh_stats[6] = (double) d->node4_count;
 	d->view.positions = d->positions; d->view.normals_uv = d->normals_uv; d->view.material_indices = d->material_indices;
 	d->view.nodes = d->nodes; d->view.nodes4 = d->nodes4; d->view.tris = d->tris; d->view.triangle_count = (uint32_t) T;
 	if (!d->gbuffer_pinned) d->gbuffer_tune = 0;
@@ -645,10 +676,10 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			}
 			const uint32_t tuning = d->trace_tune;
 			if (tuning < 2) { d->tri_vote = vote_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
-			if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill);
-			else if (d->trace_kind == 8) trace4p_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill);
-			else if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
-			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill);
+			if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 8) trace4p_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
 			if (tuning < 2) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
 			d->launches += 1;
@@ -786,36 +817,57 @@ extern "C" int risltc_cuda_traversal_counters(risltc_device_t* d, uint32_t enabl
 
 // Host-only self check of the acceleration structures (no device needed): builds the binary tree and its 4-wide, 8-bit
 // collapse for a triangle soup and verifies the invariants the traversal kernels rely on.
-extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t max_leaf, uint64_t report[6]) {
-	if (!vertices || T == 0 || !report) return fail("check_bvh: no triangles", nullptr);
-	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
-	build_bvh(vertices, T, nodes, order, max_leaf);
-	std::vector<Qbvh4NodeHost> n4;
-	const uint32_t depth = build_qbvh4(nodes, n4);
+// Invariants of a pair of acceleration structures over `vertices` (9 floats per triangle): see risltc_cuda_check_bvh in the header
+static void check_trees(const float* vertices, uint64_t T, const std::vector<BvhNodeHost>& nodes, const std::vector<uint32_t>& order,
+	const std::vector<Qbvh4NodeHost>& n4, uint32_t depth, uint64_t report[6])
+{
 	// every triangle appears in exactly one leaf slot
 	std::vector<uint32_t> seen(T, 0);
 	for (uint32_t t : order) if (t < T) seen[t]++;
 	uint64_t bad_order = 0;
 	for (uint64_t t = 0; t != T; ++t) bad_order += seen[t] != 1;
-	// leaf boxes of the binary tree by reference
+	// leaf boxes of the binary tree by reference; only nodes reachable from the root count (the device builder leaves unused slots)
 	struct LeafBox { float lo[3], hi[3]; };
 	std::vector<std::pair<int, LeafBox>> leaves;
-	uint64_t bad_binary = 0;
+	uint64_t bad_binary = 0, reachable = 0;
 	auto check_leaf = [&](int ref, const float* lo, const float* hi) {
 		const uint32_t r = ~(uint32_t) ref, first = r >> 4, count = (r & 15u) + 1u;
-		for (uint32_t s2 = first; s2 != first + count; ++s2)
+		for (uint32_t s2 = first; s2 != first + count; ++s2) {
+			if (s2 >= order.size() || order[s2] >= T) { ++bad_binary; continue; }
 			for (int v = 0; v != 3; ++v)
 				for (int k = 0; k != 3; ++k) {
 					const float x = vertices[9 * (size_t) order[s2] + 3 * v + k];
 					if (!(x >= lo[k] && x <= hi[k])) ++bad_binary;
 				}
+		}
 		LeafBox b; memcpy(b.lo, lo, 12); memcpy(b.hi, hi, 12);
 		leaves.push_back({ ref, b });
 	};
-	for (const BvhNodeHost& n : nodes) {
-		if (n.left < 0) check_leaf(n.left, n.left_lo, n.left_hi);
-		if (n.right < 0 && n.right_lo[0] <= n.right_hi[0]) check_leaf(n.right, n.right_lo, n.right_hi);
+	std::vector<int> todo(1, 0);
+	std::vector<uint8_t> visited(nodes.size(), 0);
+	while (!todo.empty()) {
+		const int i = todo.back(); todo.pop_back();
+		if (i < 0 || (size_t) i >= nodes.size() || visited[i]) { ++bad_binary; continue; }
+		visited[i] = 1; ++reachable;
+		const BvhNodeHost& n = nodes[i];
+		// an inner child's box must contain both boxes stored in that child
+		auto check_inner = [&](int child, const float* lo, const float* hi) {
+			if ((size_t) child >= nodes.size()) { ++bad_binary; return; }
+			const BvhNodeHost& c = nodes[child];
+			for (int k = 0; k != 3; ++k) {
+				if (!(lo[k] <= c.left_lo[k] + 2e-5f * fabsf(c.left_lo[k]) + 1e-6f && hi[k] >= c.left_hi[k] - 2e-5f * fabsf(c.left_hi[k]) - 1e-6f)) ++bad_binary;
+				if (c.right_lo[0] <= c.right_hi[0] && !(lo[k] <= c.right_lo[k] + 2e-5f * fabsf(c.right_lo[k]) + 1e-6f && hi[k] >= c.right_hi[k] - 2e-5f * fabsf(c.right_hi[k]) - 1e-6f)) ++bad_binary;
+			}
+			todo.push_back(child);
+		};
+		if (n.left < 0) check_leaf(n.left, n.left_lo, n.left_hi); else check_inner(n.left, n.left_lo, n.left_hi);
+		if (n.right < 0) { if (n.right_lo[0] <= n.right_hi[0]) check_leaf(n.right, n.right_lo, n.right_hi); }
+		else check_inner(n.right, n.right_lo, n.right_hi);
 	}
+	// the leaves partition the slots
+	std::vector<uint32_t> slot_seen(order.size(), 0);
+	for (const auto& l : leaves) { const uint32_t r = ~(uint32_t) l.first; for (uint32_t s2 = r >> 4; s2 != (r >> 4) + (r & 15u) + 1u && s2 < order.size(); ++s2) slot_seen[s2]++; }
+	for (uint32_t c : slot_seen) bad_binary += c != 1;
 	std::sort(leaves.begin(), leaves.end(), [](const std::pair<int, LeafBox>& a, const std::pair<int, LeafBox>& b) { return a.first < b.first; });
 	// 4-wide tree: every leaf reference appears once with a quantised box that contains the binary tree's box; every inner node is referenced once
 	uint64_t bad_wide = 0, children = 0;
@@ -841,7 +893,68 @@ extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t
 	}
 	for (size_t i = 1; i < n4.size(); ++i) bad_wide += node_refs[i] != 1;
 	for (uint32_t r : leaf_refs) bad_wide += r != 1;
-	report[0] = bad_order; report[1] = bad_binary; report[2] = bad_wide; report[3] = nodes.size(); report[4] = n4.size(); report[5] = ((uint64_t) depth << 32) | (uint64_t) (children * 100 / (n4.size() ? n4.size() : 1));
+	report[0] = bad_order; report[1] = bad_binary; report[2] = bad_wide; report[3] = reachable; report[4] = n4.size(); report[5] = ((uint64_t) depth << 32) | (uint64_t) (children * 100 / (n4.size() ? n4.size() : 1));
+}
+
+extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t max_leaf, uint64_t report[6]) {
+	if (!vertices || T == 0 || !report) return fail("check_bvh: no triangles", nullptr);
+	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
+	build_bvh(vertices, T, nodes, order, max_leaf);
+	std::vector<Qbvh4NodeHost> n4;
+	const uint32_t depth = build_qbvh4(nodes, n4);
+	check_trees(vertices, T, nodes, order, n4, depth, report);
+	return 0;
+}
+
+// The same invariants for the structures upload_scene left on the device (whichever builder made them)
+extern "C" int risltc_cuda_check_scene_bvh(risltc_device_t* d, uint64_t report[6]) {
+	if (use(d)) return 1;
+	if (!d->nodes || !d->nodes4 || !d->tris || !report) return fail("check_scene_bvh: upload_scene first", nullptr);
+	const uint64_t T = d->view.triangle_count;
+	std::vector<BvhNode> dn(d->node_count); std::vector<BvhTri> dt(T); std::vector<Qbvh4NodeHost> n4(d->node4_count); std::vector<uint32_t> qp(6 * T);
+	CU(cudaMemcpy(dn.data(), d->nodes, dn.size() * sizeof(BvhNode), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(dt.data(), d->tris, dt.size() * sizeof(BvhTri), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(n4.data(), d->nodes4, n4.size() * sizeof(Qbvh4Node), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(qp.data(), d->positions, qp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	std::vector<float> verts;
+	dequantize_mesh_for_bvh(qp.data(), T, d->dequant_factor, d->dequant_summand, verts);
+	std::vector<BvhNodeHost> nodes(dn.size()); std::vector<uint32_t> order(T);
+	uint64_t bad_records = 0;
+	for (size_t i = 0; i != dn.size(); ++i) {
+		BvhNodeHost& n = nodes[i];
+		n.left_lo[0] = dn[i].a.x; n.left_lo[1] = dn[i].a.y; n.left_lo[2] = dn[i].a.z; n.left_hi[0] = dn[i].a.w; n.left_hi[1] = dn[i].b.x; n.left_hi[2] = dn[i].b.y;
+		n.right_lo[0] = dn[i].b.z; n.right_lo[1] = dn[i].b.w; n.right_lo[2] = dn[i].c.x; n.right_hi[0] = dn[i].c.y; n.right_hi[1] = dn[i].c.z; n.right_hi[2] = dn[i].c.w;
+		n.left = dn[i].d.x; n.right = dn[i].d.y;
+	}
+	for (uint64_t slot = 0; slot != T; ++slot) {
+		uint32_t id; memcpy(&id, &dt[slot].v0.w, 4);
+		const uint32_t t = id & 0x7FFFFFFFu;
+		order[slot] = t;
+		if (t >= T) { ++bad_records; continue; }
+		// the triangle record holds v0 and the two edges of triangle t, rounded as the host builder rounds them
+		const float* v = verts.data() + 9 * (size_t) t;
+		volatile float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2], e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+		const float want[9] = { v[0], v[1], v[2], e1x, e1y, e1z, e2x, e2y, e2z };
+		const float got[9] = { dt[slot].v0.x, dt[slot].v0.y, dt[slot].v0.z, dt[slot].e1.x, dt[slot].e1.y, dt[slot].e1.z, dt[slot].e2.x, dt[slot].e2.y, dt[slot].e2.z };
+		bad_records += memcmp(want, got, sizeof(want)) != 0;
+		bad_records += (id >> 31) != (qp[6 * (size_t) t + 1] >> 31);
+	}
+	check_trees(verts.data(), T, nodes, order, n4, (uint32_t) d->bvh_stats[7] & 0xFFFFu, report);
+	report[0] += bad_records;
+	return 0;
+}
+
+extern "C" int risltc_cuda_set_bvh_builder(risltc_device_t* d, uint32_t builder) {
+	if (use(d)) return 1;
+	if (builder > RISLTC_BVH_BUILDER_AUTO) return fail("set_bvh_builder: unknown builder", nullptr);
+	d->bvh_builder = builder;
+	return 0;
+}
+
+extern "C" int risltc_cuda_bvh_stats(risltc_device_t* d, double stats[8]) {
+	if (use(d)) return 1;
+	if (!stats || !d->nodes) return fail("bvh_stats: upload_scene first", nullptr);
+	memcpy(stats, d->bvh_stats, sizeof(d->bvh_stats));
 	return 0;
 }
 
@@ -889,8 +1002,8 @@ extern "C" int risltc_cuda_kat_trace(risltc_device_t* d, const float* rays, uint
 	PixelBuffers px = {};
 	px.origin = og.p; px.ray_a = ra.p; px.ray_b = rb.p; px.ticket = ticket.p; px.pixel_count = (kind == 8) ? count / 2u : count;
 	kat_trace_fill_kernel<<<KAT_GRID(count)>>>(r.p, og.p, ra.p, rb.p, count);
-	if (kind == 8) trace4p_kernel<false><<<d->sm_count * d->trace4p_resident, 128>>>(d->view, px, count / 2u, d->tri_vote, d->refill);
-	else if (kind == 4) trace4_kernel<false><<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill);
+	if (kind == 8) trace4p_kernel<false><<<d->sm_count * d->trace4p_resident, 128>>>(d->view, px, count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+	else if (kind == 4) trace4_kernel<false><<<d->sm_count * d->trace4_resident, 128>>>(d->view, px, count, d->tri_vote, d->refill, 0x3F800000u);
 	else trace_kernel<<<d->sm_count * d->trace_resident, 128>>>(d->view, px, count, d->tri_vote);
 	kat_trace_read_kernel<<<KAT_GRID(count)>>>(rb.p, h.p, count);
 	CU(cudaDeviceSynchronize());

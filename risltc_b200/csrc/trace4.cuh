@@ -24,13 +24,21 @@ namespace RL_NS {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float min3(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
-// plane byte k of `word` -> float 1 + q * 2^-15
-__device__ __forceinline__ float q4_plane(uint32_t word, uint32_t selector) { return __uint_as_float(__byte_perm(word, 0x3F800000u, selector)); }
+// plane byte k of `word` -> float 1 + q * 2^-15. `one` holds the bits of 1.0f IN A REGISTER: PRMT takes one immediate, and
+// with the constant written here the compiler spends it on the 1.0f and rebuilds the selector in a register before each of
+// the 24 PRMTs of a node (ncu source view, round 2); the kernels receive the bits as a launch parameter instead.
+template <int CHILD>
+__device__ __forceinline__ float q4_plane(uint32_t word, uint32_t one) {
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(word), "r"(one), "n"(0x7604 | (CHILD << 4)));
+	return __uint_as_float(r);
+}
+template <int C> struct ChildIndex { static constexpr int value = C; };
 
 // COUNT = true additionally counts the rays, node visits, triangle tests and occluded rays of the launch into
 // px.counters[4..7] (bench.py's roofline_trace block: bytes per ray); the frame path runs COUNT = false unless asked.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote, uint32_t refill) {
+__global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers px, uint32_t ray_count, uint32_t tri_vote, uint32_t refill, uint32_t one) {
 	__shared__ float4 sm_stage[4][RL_TRACE_STAGE][2];
 	__shared__ int sm_nstack[RL_T4_NSTACK][128];
 	__shared__ int sm_lstack[RL_T4_LSTACK][128];
@@ -125,11 +133,10 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 			}
 			int next = -1;
 			float next_t = 0.0f;
-			#pragma unroll
-			for (int c = 0; c != 4; ++c) {
-				const uint32_t sel = 0x7604u | ((uint32_t) c << 4);
-				const float t0 = fmaxf(max3(fmaf(q4_plane(near_x, sel), sx, bx), fmaf(q4_plane(near_y, sel), sy, by), fmaf(q4_plane(near_z, sel), sz, bz)), t_min);
-				const float t1 = fminf(min3(fmaf(q4_plane(far_x, sel), sx, bx), fmaf(q4_plane(far_y, sel), sy, by), fmaf(q4_plane(far_z, sel), sz, bz)), t_max);
+			auto child = [&](auto index) {
+				constexpr int c = decltype(index)::value;
+				const float t0 = fmaxf(max3(fmaf(q4_plane<c>(near_x, one), sx, bx), fmaf(q4_plane<c>(near_y, one), sy, by), fmaf(q4_plane<c>(near_z, one), sz, bz)), t_min);
+				const float t1 = fminf(min3(fmaf(q4_plane<c>(far_x, one), sx, bx), fmaf(q4_plane<c>(far_y, one), sy, by), fmaf(q4_plane<c>(far_z, one), sz, bz)), t_max);
 				const int ref = (c == 0) ? refs.x : (c == 1) ? refs.y : (c == 2) ? refs.z : refs.w;
 				const bool hit = t0 <= t1 && ref != RL_Q4_EMPTY;
 				const bool leaf = hit && ref < 0, inner = hit && ref >= 0;
@@ -143,7 +150,8 @@ __global__ void __launch_bounds__(128) trace4_kernel(SceneView s, PixelBuffers p
 				nsp += push ? 1 : 0;
 				next = closer ? ref : next;
 				next_t = closer ? t0 : next_t;
-			}
+			};
+			child(ChildIndex<0>()); child(ChildIndex<1>()); child(ChildIndex<2>()); child(ChildIndex<3>());
 			if (next < 0 && nsp == 0 && spilled != 0) {
 				spilled -= 8; nsp = 8;
 				#pragma unroll 1
@@ -223,7 +231,7 @@ __device__ __forceinline__ bool tri_any_hit_shared(const BvhTri& tr, const TriSh
 // pair_count = pixel_count * (ray slots / 2); pair p = m * pixel_count + pixel holds the rays 2 m * pixel_count + pixel (slot A)
 // and that + pixel_count (slot B). COUNT: px.counters[4..7] += rays, node visits, triangle fetches, occluded rays.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) trace4p_kernel(SceneView s, PixelBuffers px, uint32_t pair_count, uint32_t tri_vote, uint32_t refill) {
+__global__ void __launch_bounds__(128) trace4p_kernel(SceneView s, PixelBuffers px, uint32_t pair_count, uint32_t tri_vote, uint32_t refill, uint32_t one) {
 	__shared__ float4 sm_stage[4][2 * RL_T4P_STAGE][3];
 	__shared__ int sm_nstack[RL_T4_NSTACK][128];
 	__shared__ int sm_lstack[RL_T4_LSTACK][128];
@@ -332,11 +340,10 @@ __global__ void __launch_bounds__(128) trace4p_kernel(SceneView s, PixelBuffers 
 			}
 			int next = -1;
 			float next_t = 0.0f;
-			#pragma unroll
-			for (int c = 0; c != 4; ++c) {
-				const uint32_t sel = 0x7604u | ((uint32_t) c << 4);
-				const float nx = q4_plane(near_x, sel), ny = q4_plane(near_y, sel), nz = q4_plane(near_z, sel);
-				const float fx = q4_plane(far_x, sel), fy = q4_plane(far_y, sel), fz = q4_plane(far_z, sel);
+			auto child = [&](auto index) {
+				constexpr int c = decltype(index)::value;
+				const float nx = q4_plane<c>(near_x, one), ny = q4_plane<c>(near_y, one), nz = q4_plane<c>(near_z, one);
+				const float fx = q4_plane<c>(far_x, one), fy = q4_plane<c>(far_y, one), fz = q4_plane<c>(far_z, one);
 				const float t0a = fmaxf(max3(fmaf(nx, sax, bax), fmaf(ny, say, bay), fmaf(nz, saz, baz)), t_min);
 				const float t1a = fminf(min3(fmaf(fx, sax, bax), fmaf(fy, say, bay), fmaf(fz, saz, baz)), tmax_a);
 				const float t0b = fmaxf(max3(fmaf(nx, sbx, bbx), fmaf(ny, sby, bby), fmaf(nz, sbz, bbz)), t_min);
@@ -354,7 +361,8 @@ __global__ void __launch_bounds__(128) trace4p_kernel(SceneView s, PixelBuffers 
 				nsp += push ? 1 : 0;
 				next = closer ? ref : next;
 				next_t = closer ? t0 : next_t;
-			}
+			};
+			child(ChildIndex<0>()); child(ChildIndex<1>()); child(ChildIndex<2>()); child(ChildIndex<3>());
 			if (next < 0 && nsp == 0 && spilled != 0) {
 				spilled -= 8; nsp = 8;
 				#pragma unroll 1

@@ -237,6 +237,22 @@ def many_light_room(light_count=64, box_count=200, seed=2, occluder_triangles=0,
                 width=width, height=height)
 
 
+def degenerate_soup(triangle_count=20000, seed=3):
+    """A mesh that is hard on a Morton-order builder: a third of the triangles are copies of one triangle, a third share
+    one centroid (rotated about it), the rest are small and scattered. Quantised like every other mesh."""
+    rng = np.random.default_rng(seed)
+    n = triangle_count // 3
+    base = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.2], [0.0, 1.0, 0.4]])
+    copies = np.repeat(base[None], n, axis=0) + np.array([2.0, 2.0, 1.0])
+    spun = np.stack([(base - base.mean(axis=0)) @ _random_rotation(rng).T * rng.uniform(0.1, 3.0) for _ in range(n)]) + np.array([-3.0, 1.0, 2.0])
+    rest = triangle_count - 2 * n
+    small = rng.uniform(-8.0, 8.0, (rest, 1, 3)) + rng.normal(size=(rest, 3, 3)) * rng.uniform(1e-3, 0.3, (rest, 1, 1))
+    tris = np.concatenate([copies, spun, small]).astype(np.float64)
+    normals = np.repeat(np.array([[[0.0, 0.0, 1.0]]]), triangle_count, axis=0).repeat(3, axis=1)
+    uvs = np.zeros((triangle_count, 3, 2))
+    return quantize_mesh(tris, normals, uvs, np.zeros(triangle_count, dtype=np.uint8), np.zeros(triangle_count, dtype=bool), ["m0"])
+
+
 def material_constants(materials):
     """The values the three material textures hold (scene.h:104-118): base colour rgb (linear),
     specular data (occlusion, linear roughness, metalicity), tangent-space normal (0.5, 0.5)."""

@@ -230,6 +230,58 @@ def test_kernel_alternatives_are_bit_identical(device, ltc_tables):
         device.resize(W, H, 8, 0, 1)
 
 
+def test_device_built_acceleration_structure(device, ltc_tables):
+    """The acceleration structures built by kernels (bvh_gpu.cu; the reference builds on the device, scene.c:142-406):
+    invariants of both trees, every triangle record bit-identical to the host builder's, any-hit decisions equal to the
+    oracle's bit for bit, and frames (visibility + accumulation) bit-identical to those rendered with the host-built tree."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    _, rgba, rg = ltc_tables
+    W, H = 320, 180
+    scene = scenes.many_light_room(48, 120, seed=5, occluder_triangles=30000, width=W, height=H)
+    osc = orc.OracleScene(scene, rgba, rg)
+    cs = constants_bytes([orc.make_constants(scene, W, H, orc.frame_words(f)[0], ltc_res=rgba.shape[1], ltc_layers=rgba.shape[0]) for f in range(2)])
+    rng = np.random.default_rng(9)
+    n = 6000
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, 0:3] = rng.uniform([-9, -9, 0.1], [9, 9, 5.5], (n, 3))
+    rays[n // 2:, 0:3] = rays[:n // 2, 0:3]
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d; rays[:, 3] = 1e-3; rays[:, 7] = rng.uniform(0.5, 25.0, n)
+    want = np.array([osc.any_hit(r[0:3], r[4:7], float(r[3]), float(r[7])) for r in rays], dtype=np.uint32)
+    results = {}
+    try:
+        for builder in ("host", "device"):
+            device.set_bvh_builder(builder)
+            setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records)
+            stats, report = device.bvh_stats(), device.check_scene_bvh()
+            assert stats["builder"] == builder
+            assert report["bad_order"] == 0 and report["bad_binary"] == 0 and report["bad_wide"] == 0, report
+            parity_log(f"acceleration structure, {builder} builder, {scene['mesh']['material_indices'].shape[0]} triangles: "
+                       f"build {stats['build_ms']:.1f} ms, {report['binary_nodes']} binary / {report['wide_nodes']} 4-wide nodes, depth {stats['binary_depth']} / {stats['wide_depth']}, "
+                       f"{report['children_per_node']:.2f} children per 4-wide node")
+            for kind in (8, 4, 2):
+                assert np.array_equal(device.kat_trace(rays, kind), want), f"{builder} builder, trace kernel {kind}"
+            assert np.array_equal(device.kat_any_hit(rays), want)
+            for gbuffer in ("raster", "bvh"):
+                device.set_kernels(gbuffer, "pairs")
+                device.render_frames(cs)
+                results[(builder, gbuffer)] = (device.read_visibility().copy(), device.read_accum().copy())
+        first = results[("host", "raster")]
+        for key, (vis, img) in results.items():
+            assert np.array_equal(vis, first[0]), key
+            assert np.array_equal(img.view(np.uint32), first[1].view(np.uint32)), key
+        # degenerate input for a Morton-order build: thousands of triangles with the same centroid key
+        mesh = scenes.degenerate_soup(20000, seed=3) if hasattr(scenes, "degenerate_soup") else None
+        if mesh is not None:
+            device.upload_mesh(mesh)
+            report = device.check_scene_bvh()
+            assert report["bad_order"] == 0 and report["bad_binary"] == 0 and report["bad_wide"] == 0, report
+    finally:
+        device.set_bvh_builder("auto")
+        device.set_kernels("auto", "pairs")
+
+
 def test_full_size_properties(device, ltc_tables):
     """BASELINE.json configs[1] at full size (1920x1080, 64 lights), checked through size-independent properties:
     determinism, accumulation = running mean of single frames, background / emitter pixels, fast vs exact agreement."""

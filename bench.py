@@ -101,15 +101,30 @@ def make_workload(name, lights=None):
         scene = scenes.quad_over_plane(W, H)
     else:
         scene = scenes.many_light_room(lights, boxes, seed=2, occluder_triangles=occluders, width=W, height=H, vertex_count=verts)
+        if TEXTURED:
+            scenes.add_procedural_textures(scene)
+            desc += "; materials with mip-mapped BC1 / BC5 textures (base colour, specular, normal), textureGrad per shading point"
     fits = ltc_fit.fit_ggx_ltc(64, 51, 64)
     rgba, rg = ltc_fit.quantize_fits(fits)
     return dict(name=name, desc=desc, scene=scene, fits=fits, rgba=rgba, rg=rg, W=W, H=H, spp=spp, verts=verts, lights=lights)
 
 
+# the five estimators of the reference's timing experiment (experiment_list.c:354-396): name -> light sampling, polygon sampling
+ESTIMATORS = {
+    "uniform_uniform": ("uniform", "area_turk"), "uniform_cp": ("uniform", "projected_solid_angle"), "uniform_area": ("reservoir", "area_turk"),
+    "cp_cp": ("reservoir", "projected_solid_angle"), "ltc_cp": ("reservoir", "ltc_cp"),
+}
+ESTIMATOR = "ltc_cp"
+TEXTURED = False    # --textured: procedural mip-mapped BC1 / BC5 material textures instead of flat-colour materials
+
+
 def variant_kwargs(name, verts):
     if name == "c1":
         return dict(light_sampling="uniform", technique="projected_solid_angle", min_vertices=4, max_vertices=4)
-    return dict(min_vertices=verts, max_vertices=verts)
+    kw = dict(min_vertices=verts, max_vertices=verts)
+    if ESTIMATOR != "ltc_cp":
+        kw.update(light_sampling=ESTIMATORS[ESTIMATOR][0], technique=ESTIMATORS[ESTIMATOR][1])
+    return kw
 
 
 class ClockSampler:
@@ -297,8 +312,8 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
     breakdown_note = "CUDA events around each pass, last step of the timed region"
     pass_ms[:] *= args.steps
     launches = dev.counters()["launches"] - launches0
-    if world >= 4:
-        # a device that renders a small share overlaps consecutive frames on two streams (risltc_cuda_set_frame_overlap), so the
+    if dev.frame_overlap_active():
+        # up to 4.5 M pixels a device overlaps consecutive frames on two streams (risltc_cuda_set_frame_overlap), so the
         # per-pass event intervals of the timed region overlap each other: take the breakdown from two extra, serial steps
         dev.set_frame_overlap("off")
         pass_ms[:] = 0.0
@@ -361,7 +376,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
         sm_mhz = clock_info["sm_mhz"] if clock_info and clock_info["sm_mhz"] else SM_MAX_MHZ
         peak = 2.0 * FP32_LANES_PER_SM * SM_COUNT * sm_mhz * 1e6 / 1e12 * world
         achieved = flop_per_step / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else 0.0
-        fast_path = wl["name"] != "c1"
+        fast_path = wl["name"] != "c1" and ESTIMATOR == "ltc_cp"
         hw = ncu_metrics(wl["name"]) or {}
         roofline = dict(bound="fp32", kernel=("ris_ltc3_kernel (2a: 32 RIS candidates per pixel) + winner_kernel (2b: the chosen light's PSA + LTC MIS estimator)" if fast_path
                                               else "shade_kernel<4, true> (generic fused RIS + shading kernel)"),
@@ -393,7 +408,8 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
         per_device_mb = (W * H // world) * 140 / 2 ** 20      # visibility, pick, origin, base, group, two ray slots, accumulation
         line = dict(metric="shaded light-samples/sec", value=value, unit="Gsamples/s", n_gpus=world, steps=steps, warmup=args.warmup,
                     ms_per_step=ms_max / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=wl["desc"], variant="light_reservoir (m=32) + sample_polygon_ltc_cp + mis_optimal_clamped, S=1, L=1" if wl["name"] != "c1" else "light_uniform + projected_solid_angle",
+                    config=dict(workload=wl["desc"], variant=("light_reservoir (m=32) + sample_polygon_ltc_cp + mis_optimal_clamped, S=1, L=1" if fast_path else "light_uniform + projected_solid_angle" if wl["name"] == "c1"
+                                                            else f"timing-experiment estimator {ESTIMATOR}: light_{ESTIMATORS[ESTIMATOR][0]} + sample_polygon_{ESTIMATORS[ESTIMATOR][1]} (generic kernel)"),
                                 lights=wl["lights"], triangles=triangles, width=W, height=H, spp=spp,
                                 acceleration_structure=dict(builder=bvh["builder"], build_ms=round(bvh["build_ms"], 1), device_ms=[round(x, 2) for x in bvh["device_ms"]],
                                                             wide_nodes=bvh["wide_nodes"], depth=[bvh["binary_depth"], bvh["wide_depth"]],
@@ -429,8 +445,12 @@ def main():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--stripe-height", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--estimator", default="ltc_cp", choices=sorted(ESTIMATORS), help="one of the five estimators of the reference's timing experiment (experiment_list.c:354-396); default: ours")
+    ap.add_argument("--textured", action="store_true", help="material textures (BC1 / BC5 .vkt files with mip chains through load_scene) instead of flat-colour materials")
     ap.add_argument("--emulate-stripes", type=int, default=0, help="profiling aid: render only stripe 0 of N on one GPU (the per-device share of an N-GPU run) and print its kernel times; not a bench line")
     args = ap.parse_args()
+    global ESTIMATOR, TEXTURED
+    ESTIMATOR, TEXTURED = args.estimator, args.textured
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
         args.workload = "c2" if max(world, args.gpus) == 1 else "c3"

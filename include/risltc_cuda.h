@@ -122,12 +122,14 @@ int risltc_cuda_set_kernels(risltc_device_t* device, uint32_t gbuffer, uint32_t 
 
 /* Frame overlap inside render_frames: consecutive frames alternate between two streams and two sets of per-frame buffers
  * (only the accumulation stays ordered), which fills the tails of the persistent kernels. AUTO (default): on when the
- * device renders a small share of the image (stripe_count >= 4 and at most 1.2 M pixels, where it measures faster), off
- * otherwise -- then last_kernel_ms() also times each pass in isolation. The image does not depend on the mode. Environment: RISLTC_OVERLAP=0|1. */
+ * device renders at most 4.5 M pixels (where it measures 2-19 % faster), off for larger shares (a whole 4K frame: no
+ * gain) -- only then do last_kernel_ms() / last_pass_ms() time each pass in isolation. The image does not depend on the
+ * mode. Environment: RISLTC_OVERLAP=0|1. frame_overlap_active: 1 if the frames of the next render_frames call will overlap. */
 #define RISLTC_OVERLAP_OFF 0u
 #define RISLTC_OVERLAP_ON 1u
 #define RISLTC_OVERLAP_AUTO 2u
 int risltc_cuda_set_frame_overlap(risltc_device_t* device, uint32_t mode);
+uint32_t risltc_cuda_frame_overlap_active(const risltc_device_t* device);
 
 /* Render targets (create_render_targets, main.c:246-330) for a width x height frame of which this
  * device renders the rows y with (y / stripe_height) % stripe_count == stripe_index

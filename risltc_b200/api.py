@@ -48,6 +48,7 @@ def lib():
         _lib.risltc_cuda_last_error.restype = C.c_char_p
         _lib.risltc_cuda_last_frame_ms.restype = C.c_float
         _lib.risltc_cuda_owned_rows.restype = C.c_uint32
+        _lib.risltc_cuda_frame_overlap_active.restype = C.c_uint32
         _lib.risltc_cuda_stream.restype = C.c_void_p
     return _lib
 
@@ -132,6 +133,9 @@ class Device:
 
     def set_kernels(self, gbuffer="auto", shadow="pairs"):
         _check(lib().risltc_cuda_set_kernels(self.h, C.c_uint32({"bvh": 0, "raster": 1, "auto": 2}[gbuffer]), C.c_uint32({"binary": 2, "wide": 4, "pairs": 8}[shadow])))
+
+    def frame_overlap_active(self):
+        return bool(lib().risltc_cuda_frame_overlap_active(self.h))
 
     def set_bvh_builder(self, builder="auto"):
         """Builder of the acceleration structures for the next upload_mesh: host (binned SAH), device (Morton-order radix tree) or auto."""

@@ -55,8 +55,8 @@ struct risltc_device_s {
 	uint32_t ray_slots = 0, group_slots = 0;
 	// Frame overlap: consecutive frames of a render_frames call alternate between two streams and two sets of per-frame
 	// buffers, so that the tail of one frame's persistent kernels (few warps left, SMs idling) is filled with the next
-	// frame's work; only the accumulation (resolve) of frame i waits for frame i - 1. On by default when the device renders
-	// a small share of the image (overlap_pays below), see risltc_cuda_set_frame_overlap.
+	// frame's work; only the accumulation (resolve) of frame i waits for frame i - 1. On by default up to 4.5 M pixels per
+	// device (overlap_pays below), see risltc_cuda_set_frame_overlap.
 	PixelBuffers px2 = {};
 	RasterBuffers raster2 = {};
 	bool set2_ready = false, overlap = false, overlap_pinned = false;
@@ -417,10 +417,11 @@ static int allocate_ray_buffers(risltc_device_t* d) {
 	return 0;
 }
 
-// Measured on B200 (bench.py --emulate-stripes, C2 and C3): overlapping frames wins 9-19 % when a device renders a quarter or
-// less of a frame and at most ~1 M pixels (the tails of the persistent kernels are then a fifth of a frame's time), and
-// loses 2-6 % on larger shares, where two frames' kernels mostly get in each other's way
-static bool overlap_pays(const risltc_device_t* d) { return d->stripes.stripe_count >= 4 && d->px.pixel_count <= 1200000u; }
+// Measured on B200 with the round-2 kernels (bench.py, RISLTC_OVERLAP=0|1; gpurun_out/ov_*.json): overlapping frames wins
+// 5-7 % on a whole 1080p frame (C2 33.0 -> 34.6, C4 17.2 -> 18.4 Gsamples/s), 9 % on half of one, 9-19 % on an eighth (the
+// tails of the persistent kernels are then a fifth of a frame's time), 2 % on half a 4K frame (4.1 M pixels) and nothing on
+// a whole 4K frame (8.3 M pixels), where the second set of per-frame buffers (140 bytes per pixel) is not worth its memory
+static bool overlap_pays(const risltc_device_t* d) { return d->px.pixel_count <= 4500000u; }
 
 // The second set of per-frame buffers (same sizes as the first), created the first time two frames overlap
 static int ensure_second_set(risltc_device_t* d) {
@@ -458,6 +459,8 @@ extern "C" int risltc_cuda_set_frame_overlap(risltc_device_t* d, uint32_t mode) 
 	d->overlap = (mode == RISLTC_OVERLAP_AUTO) ? overlap_pays(d) : mode == RISLTC_OVERLAP_ON;
 	return 0;
 }
+
+extern "C" uint32_t risltc_cuda_frame_overlap_active(const risltc_device_t* d) { return (d && d->overlap) ? 1u : 0u; }
 
 extern "C" int risltc_cuda_set_variant(risltc_device_t* d, const risltc_variant_t* v) {
 	if (use(d)) return 1;

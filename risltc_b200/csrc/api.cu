@@ -76,6 +76,7 @@ struct risltc_device_s {
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
 	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
+	uint32_t ris_warps = 0;          // RISLTC_RIS_WARPS=<n>: cap on the warps of the RIS kernel's one CTA per SM (tuning knob; 0 = all that fit, <= 24)
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel, two CTAs per SM: 384 (80 registers), 320 (96) or 256 (128)
 	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
 	uint32_t trace_kind = 8;      // 8: trace4p_kernel (4-wide quantised tree, the two rays of a pixel per lane), 4: trace4_kernel (one ray per lane), 2: trace_kernel (binary tree)
@@ -154,6 +155,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
 	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
+	if (const char* e = getenv("RISLTC_RIS_WARPS")) d->ris_warps = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_BVH_BUILD")) d->bvh_builder = (strcmp(e, "gpu") == 0 || strcmp(e, "device") == 0) ? 1u : (strcmp(e, "host") == 0) ? 0u : 2u;
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : (atoi(e) == 4) ? 4u : 8u;
 	*device = d;
@@ -570,7 +572,8 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 	if (specialised) {
 		const bool smem = d->view.light_count <= kMaxSmemLights;
 		const uint32_t staged = smem ? d->view.light_count : 0u;
-		const uint32_t warps = shade_fast_warps(staged);
+		uint32_t warps = shade_fast_warps(staged);
+		if (d->ris_warps && d->ris_warps < warps) warps = d->ris_warps;
 		const size_t bytes = shade_fast_smem_bytes(staged, warps);
 		// a warp owns 8x4 pixel tiles; one persistent CTA per SM
 		const uint32_t tiles_x = (d->width + 7) / 8, tile_count = tiles_x * ((d->stripes.owned_rows + 3) / 4);

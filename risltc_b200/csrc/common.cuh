@@ -154,6 +154,13 @@ __device__ __forceinline__ float unorm16(uint32_t q) {
 	const float q0 = __fmul_rn(x, c);
 	return __fmaf_rn(__fmaf_rn(-q0, 65535.0f, x), c, q0);
 }
+// x / 255 for an integer 0 <= x <= 255, correctly rounded, by the same sequence (all 256 values checked against exact
+// rational arithmetic in tests/test_oracle_identities.py): the texel decode of the material textures
+__device__ __forceinline__ float unorm8(uint32_t q) {
+	const float x = (float) q, c = 1.0f / 255.0f;
+	const float q0 = __fmul_rn(x, c);
+	return __fmaf_rn(__fmaf_rn(-q0, 255.0f, x), c, q0);
+}
 // single MUFU instructions (about 1 ulp, denormals flushed) for the paths where the rounding is free
 __device__ __forceinline__ float approx_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -74,11 +74,16 @@ __device__ __forceinline__ float4 texture_texel(const SceneView& s, const Textur
 	const size_t index = level_offset + (size_t) y * w + (size_t) x;
 	if (t.format == RL_TEXEL_RGBA32F) return __ldg((const float4*) (s.texels + t.offset) + index);
 	const uchar4 p = __ldg((const uchar4*) (s.texels + t.offset) + index);
-	if (t.format == RL_TEXEL_RGBA8_SRGB) return make_float4(__ldg(&s.srgb_table[p.x]), __ldg(&s.srgb_table[p.y]), __ldg(&s.srgb_table[p.z]), (float) p.w / 255.0f);
-	return make_float4((float) p.x / 255.0f, (float) p.y / 255.0f, (float) p.z / 255.0f, (float) p.w / 255.0f);
+	// unorm8(x) == (float) x / 255.0f for all 256 values (common.cuh)
+	if (t.format == RL_TEXEL_RGBA8_SRGB) return make_float4(__ldg(&s.srgb_table[p.x]), __ldg(&s.srgb_table[p.y]), __ldg(&s.srgb_table[p.z]), unorm8(p.w));
+	return make_float4(unorm8(p.x), unorm8(p.y), unorm8(p.z), unorm8(p.w));
 }
 __device__ __forceinline__ int texture_wrap(float coordinate, int size) {
-	const float wrapped = coordinate - floorf(coordinate / (float) size) * (float) size;
+	// coordinate / size: for a power of two the quotient is the product with the (exact) reciprocal, bit for bit -- both are
+	// the one correctly rounded value of the same real number -- and mip levels of the reference's assets always are
+	const float fs = (float) size;
+	const float quotient = ((size & (size - 1)) == 0) ? coordinate * __uint_as_float(0x7F000000u - __float_as_uint(fs)) : coordinate / fs;
+	const float wrapped = coordinate - floorf(quotient) * fs;
 	const int i = (int) wrapped;
 	return (i >= size || i < 0) ? 0 : i;
 }

@@ -119,3 +119,36 @@ def test_accumulation_is_a_running_mean():
     for k in range(5):
         orc.lib().orc_accum_pass(acc.ctypes.data_as(C.c_void_p), frames[k].ctypes.data_as(C.c_void_p), C.c_uint32(k), C.c_uint64(16))
     assert np.allclose(acc, frames.mean(axis=0), rtol=1e-6)
+
+
+def test_unorm_decodes_are_exactly_rounded_quotients():
+    """The kernels decode x / 255 (texels) and x / 65535 (vertex attributes, LTC tables) as q0 = x * c, q0 + (x - q0 * d) * c
+    with c = fl(1 / d) and fused multiply-adds (risltc_b200/csrc/common.cuh: unorm8, unorm16) instead of an IEEE division.
+    Checked here against exact rational arithmetic for every input: the sequence returns the correctly rounded quotient."""
+    from fractions import Fraction as F
+    import math
+
+    def fl32(fr):
+        if fr == 0:
+            return F(0)
+        sign, a = (1 if fr > 0 else -1), abs(fr)
+        e = math.floor(math.log2(float(a)))
+        while F(2) ** e > a:
+            e -= 1
+        while F(2) ** (e + 1) <= a:
+            e += 1
+        ulp = F(2) ** (e - 23)
+        q = a / ulp
+        n = q.numerator // q.denominator
+        rem = q - n
+        if rem > F(1, 2) or (rem == F(1, 2) and n % 2 == 1):
+            n += 1
+        return sign * n * ulp
+
+    for d in (255, 65535):
+        c = fl32(F(1, d))
+        assert c == F(float(np.float32(1.0) / np.float32(d)))
+        for x in range(d + 1):
+            q0 = fl32(F(x) * c)
+            r = fl32(fl32(-q0 * d + x) * c + q0)      # two fused multiply-adds: each rounds once
+            assert r == fl32(F(x, d)), (x, d)

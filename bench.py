@@ -97,6 +97,9 @@ def make_workload(name, lights=None):
         spp = C5_SPP
     else:
         desc, lights, boxes, occluders, W, H, spp, verts = WORKLOADS[name]
+    if LIGHT_VERTICES and name != "c1":
+        verts = LIGHT_VERTICES
+        desc += f"; lights with {verts} vertices"
     if name == "c1":
         scene = scenes.quad_over_plane(W, H)
     else:
@@ -115,6 +118,7 @@ ESTIMATORS = {
     "cp_cp": ("reservoir", "projected_solid_angle"), "ltc_cp": ("reservoir", "ltc_cp"),
 }
 ESTIMATOR = "ltc_cp"
+LIGHT_VERTICES = 0  # --light-vertices 4: quad lights instead of the workload's triangles (reference variant ris_ltc_v4)
 TEXTURED = False    # --textured: procedural mip-mapped BC1 / BC5 material textures instead of flat-colour materials
 
 
@@ -179,7 +183,7 @@ def cpu_reference_run(wl, frames):
     if osc is None:
         osc = wl["_oracle_scene"] = orc.OracleScene(wl["scene"], wl["rgba"], wl["rg"])   # BVH build: not part of the timed work
     cs = [orc.make_constants(wl["scene"], W, H, orc.frame_words(f)[0]) for f in range(frames)]
-    ref_name = {"c1": "uni_psa_v4"}.get(wl["name"], "ris_ltc_v3")
+    ref_name = {"c1": "uni_psa_v4"}.get(wl["name"], "ris_ltc_v4" if wl["verts"] == 4 else "ris_ltc_v3")
     light_samples = 1
     if ref.available(ref_name):
         r = ref.RefShading(ref_name); r.bind(osc)
@@ -378,7 +382,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
         achieved = flop_per_step / (shade_ms * 1e-3) / 1e12 if shade_ms > 0 else 0.0
         fast_path = wl["name"] != "c1" and ESTIMATOR == "ltc_cp"
         hw = ncu_metrics(wl["name"]) or {}
-        roofline = dict(bound="fp32", kernel=("ris_ltc3_kernel (2a: 32 RIS candidates per pixel) + winner_kernel (2b: the chosen light's PSA + LTC MIS estimator)" if fast_path
+        roofline = dict(bound="fp32", kernel=(("ris_ltc4_kernel" if wl["verts"] == 4 else "ris_ltc3_kernel") + " (2a: 32 RIS candidates per pixel) + winner_kernel (2b: the chosen light's PSA + LTC MIS estimator)" if fast_path
                                               else "shade_kernel<4, true> (generic fused RIS + shading kernel)"),
                         achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak if peak else None,
                         traffic=hw.get("shading_dram_bytes_per_launch"), traffic_source=hw.get("source"),
@@ -446,11 +450,12 @@ def main():
     ap.add_argument("--stripe-height", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--estimator", default="ltc_cp", choices=sorted(ESTIMATORS), help="one of the five estimators of the reference's timing experiment (experiment_list.c:354-396); default: ours")
+    ap.add_argument("--light-vertices", type=int, default=0, choices=[0, 3, 4], help="4: quad lights (the specialised kernels' second instantiation)")
     ap.add_argument("--textured", action="store_true", help="material textures (BC1 / BC5 .vkt files with mip chains through load_scene) instead of flat-colour materials")
     ap.add_argument("--emulate-stripes", type=int, default=0, help="profiling aid: render only stripe 0 of N on one GPU (the per-device share of an N-GPU run) and print its kernel times; not a bench line")
     args = ap.parse_args()
-    global ESTIMATOR, TEXTURED
-    ESTIMATOR, TEXTURED = args.estimator, args.textured
+    global ESTIMATOR, TEXTURED, LIGHT_VERTICES
+    ESTIMATOR, TEXTURED, LIGHT_VERTICES = args.estimator, args.textured, args.light_vertices
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
         args.workload = "c2" if max(world, args.gpus) == 1 else "c3"

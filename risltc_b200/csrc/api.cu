@@ -133,6 +133,10 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	CU(cudaFuncSetAttribute(ris_ltc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
+	CU(cudaFuncSetAttribute(ris_ltc4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM_LIMIT));
 	d->sm_count = prop.multiProcessorCount;
 	CU(cudaMalloc(&d->px.counters, 8 * sizeof(unsigned long long)));
 	CU(cudaMemset(d->px.counters, 0, 8 * sizeof(unsigned long long)));
@@ -364,17 +368,18 @@ extern "C" int risltc_cuda_upload_lights(risltc_device_t* d, const void* records
 		cudaFree(d->lights); d->lights = nullptr;
 		cudaFree(d->lights_tri); d->lights_tri = nullptr;
 		CU(cudaMalloc(&d->lights, bytes));
-		if (max_vertex_count == 3) CU(cudaMalloc(&d->lights_tri, (size_t) light_count * 48));
+		if (max_vertex_count <= 4) CU(cudaMalloc(&d->lights_tri, (size_t) light_count * 16 * max_vertex_count));
 	}
 	CU(cudaMemcpyAsync(d->lights, records, bytes, cudaMemcpyHostToDevice, d->stream));
-	if (max_vertex_count == 3) {
-		// the candidate loop's view of a triangle light: 48 bytes {v0 | Le.r, v1 | Le.g, v2 | Le.b}
+	if (max_vertex_count <= 4) {
+		// the candidate loop's view of a triangle / quad light: 48 bytes {v0 | Le.r, v1 | Le.g, v2 | Le.b} (+ {v3 | 0})
+		const uint32_t V = max_vertex_count;
 		const float* r = (const float*) records;
-		std::vector<float> packed((size_t) light_count * 12);
-		for (uint32_t i = 0; i != light_count; ++i, r += 24)
-			for (int v = 0; v != 3; ++v) {
-				memcpy(&packed[12 * (size_t) i + 4 * v], r + 12 + 4 * v, 12);
-				packed[12 * (size_t) i + 4 * v + 3] = r[v];
+		std::vector<float> packed((size_t) light_count * 4 * V);
+		for (uint32_t i = 0; i != light_count; ++i, r += 12 + 4 * V)
+			for (uint32_t v = 0; v != V; ++v) {
+				memcpy(&packed[4 * V * (size_t) i + 4 * v], r + 12 + 4 * v, 12);
+				packed[4 * V * (size_t) i + 4 * v + 3] = (v < 3u) ? r[v] : 0.0f;
 			}
 		CU(cudaMemcpyAsync(d->lights_tri, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, d->stream));
 		CU(cudaStreamSynchronize(d->stream));   // `packed` is pageable stack-owned memory
@@ -568,19 +573,27 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 	const bool defer = deferred_rays(v);
 	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
 		&& v.mis_heuristic == MIS_OPTIMAL_CLAMPED && v.sample_count == 1u && v.light_samples == 1u && v.fast_atan == 0u
-		&& v.min_light_vertices == 3u && v.max_light_vertices == 3u && d->view.lights_tri != nullptr;
+		&& (v.max_light_vertices == 3u || v.max_light_vertices == 4u) && v.min_light_vertices == v.max_light_vertices
+		&& d->view.light_stride4 == 3u + v.max_light_vertices && d->view.lights_tri != nullptr;
 	if (specialised) {
-		const bool smem = d->view.light_count <= kMaxSmemLights;
+		const bool quads = v.max_light_vertices == 4u;
+		const bool smem = d->view.light_count <= (quads ? kMaxSmemLights * 3u / 5u : kMaxSmemLights);
 		const uint32_t staged = smem ? d->view.light_count : 0u;
-		uint32_t warps = shade_fast_warps(staged);
+		uint32_t warps = quads ? shade_fast4_warps(staged) : shade_fast_warps(staged);
 		if (d->ris_warps && d->ris_warps < warps) warps = d->ris_warps;
-		const size_t bytes = shade_fast_smem_bytes(staged, warps);
+		const size_t bytes = quads ? shade_fast4_smem_bytes(staged, warps) : shade_fast_smem_bytes(staged, warps);
 		// a warp owns 8x4 pixel tiles; one persistent CTA per SM
 		const uint32_t tiles_x = (d->width + 7) / 8, tile_count = tiles_x * ((d->stripes.owned_rows + 3) / 4);
 		uint32_t ctas = (uint32_t) d->sm_count;
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
 		const bool textured = d->view.textures != nullptr;
-		if (smem && !textured) ris_ltc3_kernel<true, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		if (quads) {
+			if (smem && !textured) ris_ltc4_kernel<true, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (!textured) ris_ltc4_kernel<false, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (smem) ris_ltc4_kernel<true, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else ris_ltc4_kernel<false, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+		}
+		else if (smem && !textured) ris_ltc3_kernel<true, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		else if (!textured) ris_ltc3_kernel<false, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		else if (smem) ris_ltc3_kernel<true, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 		else ris_ltc3_kernel<false, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
@@ -590,7 +603,8 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
 			uint32_t wctas = 2u * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (d->winner_cr) { if (rl_launch_winner_cr(d->view, f, d->stripes, px, tiles_x, tile_count, std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), stream)) return 1; }
+			if (quads) winner_kernel<384, 768, 4><<<std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (d->winner_cr) { if (rl_launch_winner_cr(d->view, f, d->stripes, px, tiles_x, tile_count, std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), stream)) return 1; }
 			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else if (threads == 320) winner_kernel<320, 640><<<wctas, 320, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);

@@ -277,6 +277,209 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same kernel for QUAD lights (every light has four vertices: MIN = MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 4, the shape
+// polygonal_light.c creates by default and the V = 4 variants of the comparison matrix use). What changes is the size of
+// things: table records {v0 | Le.r, v1 | Le.g, v2 | Le.b, v3 | 0}, a four-edge form factor, and the horizon clip of a quad
+// (up to five vertices, rare: a small walk through local arrays). Strides are chosen ODD in 16-byte units, so that
+// consecutive slots / random records spread over all eight 16-byte bank groups like the triangle kernel's 48-byte records
+// do: table records are 80 bytes apart in shared memory (the fifth vector is padding), queue items hold the twelve
+// coordinates in 48 bytes and their destination slots live in an array of their own. (A first version with 64-byte
+// records and items ran into four-way bank conflicts on every gather, push and drain: 2.1 instead of 0.9 ms per C2 frame.)
+#define RL_ITEM_WORDS4 12     // p0..p3: three 16-byte accesses
+#define RL_TABLE_STRIDE4 5u   // float4 per staged quad light
+#define RL_WARP_WORDS4 (2 * RL_CHUNK * 32 + RL_QUEUE * RL_ITEM_WORDS4 + RL_QUEUE)   // 8.5 KB per warp
+__host__ __device__ inline size_t shade_fast4_smem_bytes(uint32_t staged_lights, uint32_t warps) {
+	return (size_t) staged_lights * 16 * RL_TABLE_STRIDE4 + (size_t) warps * RL_WARP_WORDS4 * 4;
+}
+__host__ inline uint32_t shade_fast4_warps(uint32_t staged_lights) {
+	uint32_t warps = (RL_SMEM_LIMIT - staged_lights * 16u * RL_TABLE_STRIDE4) / (RL_WARP_WORDS4 * 4u);
+	return warps > RL_FAST_MAX_WARPS ? RL_FAST_MAX_WARPS : warps;
+}
+
+// |calculate_ltc| of a quad that lies entirely above the horizon
+__device__ __forceinline__ float ff_above4(float3 p0, float3 p1, float3 p2, float3 p3) {
+	float3 a = unit3(p0), b = unit3(p1), c = unit3(p2), d = unit3(p3);
+	float xab = fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)), xbc = fmaf(b.x, c.x, fmaf(b.y, c.y, b.z * c.z));
+	float xcd = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z)), xda = fmaf(d.x, a.x, fmaf(d.y, a.y, d.z * a.z));
+	float tab = ff_fit(fabsf(xab)), tbc = ff_fit(fabsf(xbc)), tcd = ff_fit(fabsf(xcd)), tda = ff_fit(fabsf(xda));
+	if (fminf(fminf(xab, xbc), fminf(xcd, xda)) <= 0.0f) {
+		tab = (xab > 0.0f) ? tab : ff_obtuse(xab, tab);
+		tbc = (xbc > 0.0f) ? tbc : ff_obtuse(xbc, tbc);
+		tcd = (xcd > 0.0f) ? tcd : ff_obtuse(xcd, tcd);
+		tda = (xda > 0.0f) ? tda : ff_obtuse(xda, tda);
+	}
+	float sum = fmaf(a.x, b.y, -a.y * b.x) * tab;
+	sum = fmaf(fmaf(b.x, c.y, -b.y * c.x), tbc, sum);
+	sum = fmaf(fmaf(c.x, d.y, -c.y * d.x), tcd, sum);
+	sum = fmaf(fmaf(d.x, a.y, -d.y * a.x), tda, sum);
+	return fabsf(sum);
+}
+// A quad that crosses the horizon: the clipped polygon (polygon_clipping.glsl:35-225 for vertex_count == 4; the start of
+// the walk does not matter for the absolute value of the closed edge sum), three to five vertices
+__device__ __noinline__ float ff_clipped_quad(float3 p0, float3 p1, float3 p2, float3 p3) {
+	const float3 v[4] = { p0, p1, p2, p3 };
+	float3 out[6];
+	int n = 0;
+	#pragma unroll
+	for (int i = 0; i != 4; ++i) {
+		const int j = (i + 1) & 3;
+		const bool a = v[i].z > 0.0f, b = v[j].z > 0.0f;
+		if (a) out[n++] = unit3(v[i]);
+		if (a != b) out[n++] = unit3(horizon_crossing(v[i], v[j]));
+	}
+	if (n < 3) return 0.0f;
+	float sum = 0.0f;
+	for (int k = 0; k != n; ++k) sum += ff_edge(out[k], out[(k + 1 == n) ? 0 : k + 1]);
+	return fabsf(sum);
+}
+__device__ __forceinline__ void push_quad(float* queue, uint32_t* queue_dest, uint32_t& count_above, uint32_t& count_crossing, uint32_t lt_mask,
+	float3 p0, float3 p1, float3 p2, float3 p3, uint32_t dest)
+{
+	const float zmin = fminf(fminf(p0.z, p1.z), fminf(p2.z, p3.z)), zmax = fmaxf(fmaxf(p0.z, p1.z), fmaxf(p2.z, p3.z));
+	const bool above = zmin > 0.0f, crossing = !above && zmax > 0.0f;
+	const unsigned ballot_above = __ballot_sync(0xFFFFFFFFu, above), ballot_crossing = __ballot_sync(0xFFFFFFFFu, crossing);
+	if (above || crossing) {
+		const uint32_t rank = __popc((above ? ballot_above : ballot_crossing) & lt_mask);
+		const uint32_t slot = above ? count_above + rank : (RL_QUEUE - 1u) - count_crossing - rank;
+		float4* item = (float4*) (queue + slot * RL_ITEM_WORDS4);
+		item[0] = make_float4(p0.x, p0.y, p0.z, p1.x);
+		item[1] = make_float4(p1.y, p1.z, p2.x, p2.y);
+		item[2] = make_float4(p2.z, p3.x, p3.y, p3.z);
+		queue_dest[slot] = dest;
+	}
+	count_above += __popc(ballot_above);
+	count_crossing += __popc(ballot_crossing);
+}
+template <bool ABOVE>
+__device__ __forceinline__ void drain4(const float* queue, const uint32_t* queue_dest, float* ff, uint32_t first, uint32_t n, uint32_t lane) {
+	__syncwarp();
+	if (lane < n) {
+		const float4* item = (const float4*) (queue + (first + lane) * RL_ITEM_WORDS4);
+		const float4 a = item[0], b = item[1], c = item[2];
+		const uint32_t dest = queue_dest[first + lane];
+		const float3 p0 = mk3(a.x, a.y, a.z), p1 = mk3(a.w, b.x, b.y), p2 = mk3(b.z, b.w, c.x), p3 = mk3(c.y, c.z, c.w);
+		ff[dest] = ABOVE ? ff_above4(p0, p1, p2, p3) : ff_clipped_quad(p0, p1, p2, p3);
+	}
+	__syncwarp();
+}
+
+template <bool SMEM, bool TEXTURED>
+__global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc4_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+	extern __shared__ float4 sm_base[];
+	const int N = (int) s.light_count;
+	const uint32_t staged = SMEM ? (uint32_t) N : 0u;
+	if (SMEM) for (uint32_t i = threadIdx.x; i < 4u * staged; i += blockDim.x) sm_base[(i >> 2) * RL_TABLE_STRIDE4 + (i & 3u)] = __ldg(&s.lights_tri[i]);
+	__syncthreads();
+	const float4* table = SMEM ? sm_base : s.lights_tri;
+	const uint32_t table_stride = SMEM ? RL_TABLE_STRIDE4 : 4u;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t lt_mask = (1u << lane) - 1u;
+	float* ff = (float*) (sm_base + RL_TABLE_STRIDE4 * staged) + warp * RL_WARP_WORDS4;   // [2][RL_CHUNK][32]
+	float* queue = ff + 2 * RL_CHUNK * 32;                                                 // [RL_QUEUE][RL_ITEM_WORDS4]
+	uint32_t* queue_dest = (uint32_t*) (queue + RL_QUEUE * RL_ITEM_WORDS4);                // [RL_QUEUE]
+	const float Nf = (float) N, index_scale = Nf * 2.3283064365386962890625e-10f;
+	uint32_t shaded = 0;
+	while (true) {
+		uint32_t tile = 0;
+		if (lane == 0) tile = atomicAdd(&out.ticket[1], 1u);
+		tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+		if (tile >= tile_count) break;
+		const uint32_t x = (tile % tiles_x) * 8u + (lane & 7u);
+		const uint32_t row = (tile / tiles_x) * 4u + (lane >> 3);
+		const bool inside = x < f.width && row < st.owned_rows;
+		const uint32_t y = st.global_row(inside ? row : 0u);
+		const uint32_t pixel = row * f.width + x;
+		const uint32_t prim = (inside && y < f.height) ? out.visibility[pixel] : 0xFFFFFFFEu;
+		const bool active = prim != 0xFFFFFFFFu && (prim >> 31) == 0u;
+		if (inside && y < f.height && !active) {
+			float v = (prim == 0xFFFFFFFFu) ? 0.0f : 1.0f;
+			out.base[pixel] = make_float4(v, v, v, (prim == 0xFFFFFFFFu) ? 1.0f : 0.0f);
+			out.origin[pixel] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+		}
+		if (!__any_sync(0xFFFFFFFFu, active)) continue;
+		ShadingPoint sp;
+		LtcFrame ltc;
+		ltc.rx = ltc.ry = ltc.rz = ltc.t = mk3(0.0f, 0.0f, 0.0f);
+		ltc.s00 = ltc.s02 = ltc.s11 = ltc.s20 = ltc.s22 = 0.0f;
+		uint32_t seed = 0;
+		if (active) {
+			++shaded;
+			sp = reconstruct_shading_point<TEXTURED>(s, f, prim, primary_ray(f, x, y));
+			float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+			ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+			seed = noise_seed(x, y, f.width, f.frame_word);
+			const size_t n = out.pixel_count;
+			out.shade[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, sp.roughness);
+			out.shade[n + pixel] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, ltc.s00);
+			out.shade[2 * n + pixel] = make_float4(sp.diffuse_albedo.x, sp.diffuse_albedo.y, sp.diffuse_albedo.z, -ltc.s20);
+			out.shade[3 * n + pixel] = make_float4(sp.fresnel_0.x, sp.fresnel_0.y, sp.fresnel_0.z, ltc.s11);
+			out.shade[4 * n + pixel] = make_float4(sp.outgoing.x, sp.outgoing.y, sp.outgoing.z, ltc.s02);
+			out.shade[5 * n + pixel] = make_float4(ltc.s22, ltc.albedo, 0.0f, 0.0f);
+		}
+		float w_sum = 0.0f, chosen_p_hat = 0.0f;
+		int chosen = -1;
+		for (int chunk = 0; chunk != 32 / RL_CHUNK; ++chunk) {
+			const uint32_t chunk_seed = seed;
+			uint32_t count_above = 0, count_crossing = 0;   // warp-uniform
+			uint32_t dest = lane;
+			#pragma unroll
+			for (int i = 0; i != 2 * RL_CHUNK / 4; ++i) ((float4*) ff)[i * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			__syncwarp();
+			#pragma unroll 1
+			for (int j = 0; j != RL_CHUNK; ++j) {
+				seed = 1664525u * seed + 1013904223u;
+				int idx = min((int) (__uint2float_rn(seed) * index_scale), N - 1);
+				seed = 1664525u * seed + 1013904223u;   // the reservoir's draw, consumed in pass 2
+				float3 p[4], q[4];
+				#pragma unroll
+				for (int k = 0; k != 4; ++k) {
+					const float4 A = table[table_stride * idx + k];
+					p[k].x = fmaf(ltc.rx.x, A.x, fmaf(ltc.rx.y, A.y, fmaf(ltc.rx.z, A.z, ltc.t.x)));
+					p[k].y = fmaf(ltc.ry.x, A.x, fmaf(ltc.ry.y, A.y, fmaf(ltc.ry.z, A.z, ltc.t.y)));
+					p[k].z = fmaf(ltc.rz.x, A.x, fmaf(ltc.rz.y, A.y, fmaf(ltc.rz.z, A.z, ltc.t.z)));
+					q[k] = mk3(fmaf(ltc.s00, p[k].x, ltc.s02 * p[k].z), ltc.s11 * p[k].y, fmaf(ltc.s20, p[k].x, ltc.s22 * p[k].z));
+				}
+				push_quad(queue, queue_dest, count_above, count_crossing, lt_mask, p[0], p[1], p[2], p[3], dest);
+				push_quad(queue, queue_dest, count_above, count_crossing, lt_mask, q[0], q[1], q[2], q[3], dest + RL_CHUNK * 32u);
+				dest += 32u;
+				while (count_above >= 32u) { count_above -= 32u; drain4<true>(queue, queue_dest, ff, count_above, 32u, lane); }
+				while (count_crossing >= 32u) { count_crossing -= 32u; drain4<false>(queue, queue_dest, ff, RL_QUEUE - 32u - count_crossing, 32u, lane); }
+			}
+			if (count_above) drain4<true>(queue, queue_dest, ff, 0u, count_above, lane);
+			if (count_crossing) drain4<false>(queue, queue_dest, ff, RL_QUEUE - count_crossing, count_crossing, lane);
+			__syncwarp();
+			if (active) {
+				uint32_t replay = chunk_seed;
+				#pragma unroll 4
+				for (int j = 0; j != RL_CHUNK; ++j) {
+					replay = 1664525u * replay + 1013904223u;
+					int idx = min((int) (__uint2float_rn(replay) * index_scale), N - 1);
+					replay = 1664525u * replay + 1013904223u;
+					float r = __uint2float_rn(replay) * 2.3283064365386962890625e-10f;
+					const float* rec = (const float*) (table + table_stride * idx);
+					float fd = ff[j * 32 + lane], fs = ff[(RL_CHUNK + j) * 32 + lane] * ltc.albedo;
+					float cr = fmaf(sp.diffuse_albedo.x, fd, fs) * rec[3], cg = fmaf(sp.diffuse_albedo.y, fd, fs) * rec[7], cb = fmaf(sp.diffuse_albedo.z, fd, fs) * rec[11];
+					float p_hat = approx_sqrt(fmaf(cr, cr, fmaf(cg, cg, cb * cb)));
+					float w = p_hat * Nf;
+					w_sum += w;
+					if (w > 0.0f && r * w_sum < w) { chosen = idx; chosen_p_hat = p_hat; }
+				}
+			}
+			__syncwarp();
+		}
+		if (active) {
+			float scale = (chosen < 0 || chosen_p_hat == 0.0f) ? 0.0f : w_sum / (32.0f * chosen_p_hat);
+			out.pick[pixel] = make_uint4((uint32_t) chosen, __float_as_uint(scale), seed, 0u);
+		}
+	}
+	unsigned total = __reduce_add_sync(0xFFFFFFFFu, shaded);
+	if (lane == 0 && total) {
+		atomicAdd(&out.counters[0], (unsigned long long) total);
+		atomicAdd(&out.counters[3], 32ull * total);
+	}
+}
+
 // clip_to_horizon<4> for a triangle (vertex count == MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING == 3) without the dynamically
 // indexed walk: the same vertices in the same order (polygon_clipping.glsl:56-75: row 0 of the rotation table), every slot
 // addressed statically so that the polygon stays in registers. horizon_crossing(v_i, v_i+1) per crossed edge, as there.
@@ -310,11 +513,14 @@ __device__ __forceinline__ uint32_t clip_triangle_to_horizon(float3 (&v)[4]) {
 // (496-byte frames x 768 threads = 380 KB per SM, more than L1 holds): ncu showed 48 M + 47 M local sectors per launch and
 // 477 MB of DRAM writes against 232 MB algorithmic (profiles/r1_ncu_final_kernels.txt).
 // The draws keep the reference's order (diffuse pair, then specular pair only if its solid angle is positive).
-#define RL_POLY_WORDS 24   // vc, v[4], e[4], inner0, sector[4], total
-template <int RL_WIN_THREADS, int RL_WIN_RESIDENT_THREADS>
+// V = vertices of every light (3: triangles, the bench configurations; 4: quads, the reference's default light shape --
+// the clipped polygon then has up to P = V + 1 vertices and the clip is the generic rotation-table walk of shading.cuh).
+template <int RL_WIN_THREADS, int RL_WIN_RESIDENT_THREADS, int V = 3>
 __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+	constexpr int P = V + 1;
+	constexpr int RL_POLY_WORDS = 5 * P + 4;   // vc, v[P], e[P], inner0, sector[P], total
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
-	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, 3u, 3u };
+	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, (uint32_t) V, (uint32_t) V };
 	// a warp owns 8x4 pixel tiles; the CTA takes `warps` neighbouring tiles per round through a ticket (barriers inside)
 	__shared__ uint32_t sm_base;
 	__shared__ float sm_poly[RL_POLY_WORDS][RL_WIN_THREADS];
@@ -371,48 +577,50 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 			__syncthreads();
 			bool prepared = false;
 			if (live && (tech == 0 || polygon_d)) {
-				float3 pv[4];
+				float3 pv[P];
 				#pragma unroll
-				for (int i = 0; i != 3; ++i) {
+				for (int i = 0; i != V; ++i) {
 					const float4 w = __ldg(light_record + 3 + i);
 					pv[i] = tech ? to_cosine_space(ltc, mk3(w.x, w.y, w.z), t.flip) : to_shading_space(ltc, mk3(w.x, w.y, w.z), t.flip);
 				}
-				pv[3] = mk3(0.0f, 0.0f, 0.0f);
-				const uint32_t vc = clip_triangle_to_horizon(pv);
+				pv[V] = mk3(0.0f, 0.0f, 0.0f);
+				uint32_t vc;
+				if (V == 3) vc = clip_triangle_to_horizon(reinterpret_cast<float3 (&)[4]>(pv));
+				else vc = clip_to_horizon<P>((uint32_t) V, pv, (uint32_t) V);
 				if (tech == 0) { polygon_d = vc != 0u; live = polygon_d; }
 				if (vc != 0u) {
-					PsaPolygon<4> p;
+					PsaPolygon<P> p;
 					#pragma unroll
-					for (int i = 0; i != 4; ++i) { p.v[i] = mk2(0.0f, 0.0f); p.e[i] = mk2(0.0f, 0.0f); p.sector[i] = 0.0f; }
-					psa_prepare<4, false>(p, vc, pv);
+					for (int i = 0; i != P; ++i) { p.v[i] = mk2(0.0f, 0.0f); p.e[i] = mk2(0.0f, 0.0f); p.sector[i] = 0.0f; }
+					psa_prepare<P, false>(p, vc, pv);
 					if (tech == 0) { total_d = p.total; live = total_d != 0.0f; }
 					else total_s = p.total;
 					prepared = live && (tech == 0 || total_s > 0.0f);
 					if (prepared) {
 						RL_POLY(0) = __uint_as_float(p.vc);
 						#pragma unroll
-						for (int i = 0; i != 4; ++i) {
+						for (int i = 0; i != P; ++i) {
 							RL_POLY(1 + 2 * i) = p.v[i].x; RL_POLY(2 + 2 * i) = p.v[i].y;
-							RL_POLY(9 + 2 * i) = p.e[i].x; RL_POLY(10 + 2 * i) = p.e[i].y;
-							RL_POLY(19 + i) = p.sector[i];
+							RL_POLY(1 + 2 * P + 2 * i) = p.e[i].x; RL_POLY(2 + 2 * P + 2 * i) = p.e[i].y;
+							RL_POLY(3 + 4 * P + i) = p.sector[i];
 						}
-						RL_POLY(17) = p.inner0.x; RL_POLY(18) = p.inner0.y; RL_POLY(23) = p.total;
+						RL_POLY(1 + 4 * P) = p.inner0.x; RL_POLY(2 + 4 * P) = p.inner0.y; RL_POLY(3 + 5 * P) = p.total;
 					}
 				}
 			}
 			__syncthreads();
 			if (prepared) {
-				PsaPolygon<4> p;
+				PsaPolygon<P> p;
 				p.vc = __float_as_uint(RL_POLY(0));
 				#pragma unroll
-				for (int i = 0; i != 4; ++i) {
+				for (int i = 0; i != P; ++i) {
 					p.v[i] = mk2(RL_POLY(1 + 2 * i), RL_POLY(2 + 2 * i));
-					p.e[i] = mk2(RL_POLY(9 + 2 * i), RL_POLY(10 + 2 * i));
-					p.sector[i] = RL_POLY(19 + i);
+					p.e[i] = mk2(RL_POLY(1 + 2 * P + 2 * i), RL_POLY(2 + 2 * P + 2 * i));
+					p.sector[i] = RL_POLY(3 + 4 * P + i);
 				}
-				p.inner0 = mk2(RL_POLY(17), RL_POLY(18)); p.total = RL_POLY(23);
+				p.inner0 = mk2(RL_POLY(1 + 4 * P), RL_POLY(2 + 4 * P)); p.total = RL_POLY(3 + 5 * P);
 				const float u0 = noise_next(seed), u1 = noise_next(seed);
-				const float3 d = psa_sample<4, false, false>(p, u0, u1);
+				const float3 d = psa_sample<P, false, false>(p, u0, u1);
 				if (tech == 0) dir0 = d;
 				else dir1 = cosine_to_shading_dir(ltc, d);
 			}
@@ -421,15 +629,15 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 		// ---- (D): densities, BRDF, MIS (shading_pass.frag.glsl:373-394); the rays are recorded for the trace kernel
 		float3 carry = mk3(0.0f, 0.0f, 0.0f);
 		if (live) {
-			Light<3> light;
+			Light<V> light;
 			const float4 la = __ldg(light_record), lb = __ldg(light_record + 1);
-			light.radiance = mk3(la.x, la.y, la.z); light.plane = lb; light.count = 3u;
+			light.radiance = mk3(la.x, la.y, la.z); light.plane = lb; light.count = (uint32_t) V;
 			technique_weights(t, sp, ltc.albedo, total_d, total_s, light.radiance, false);
 			const int techniques = (total_s > 0.0f) ? 2 : 1;
 			for (int j = 0; j != techniques; ++j) {
 				RayRequest ray; bool side_visible; float3 if_occluded;
 				ray.dir = mk3(0.0f, 0.0f, 1.0f); ray.t_max = -1.0f; ray.if_visible = mk3(0.0f, 0.0f, 0.0f);
-				if (!technique_sample<3>(t, sp, ltc, light, var, j, j ? dir1 : dir0, f.mis_visibility_estimate, true, ray, side_visible, if_occluded)) continue;
+				if (!technique_sample<V>(t, sp, ltc, light, var, j, j ? dir1 : dir0, f.mis_visibility_estimate, true, ray, side_visible, if_occluded)) continue;
 				if (!side_visible) { carry = add3(carry, if_occluded); continue; }
 				out.ray_a[(size_t) j * out.pixel_count + pixel] = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.t_max);
 				out.ray_b[(size_t) j * out.pixel_count + pixel] = make_float4(ray.if_visible.x, ray.if_visible.y, ray.if_visible.z, 1.0f);

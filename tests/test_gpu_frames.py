@@ -107,6 +107,22 @@ def test_room_variants(device, ltc_tables, kw, precision):
 
 
 
+@pytest.mark.parametrize("frames", [1, 4, 16])
+def test_quad_lights_on_the_specialised_kernels(device, ltc_tables, frames):
+    """The default estimator on QUAD lights (MIN = MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 4, the shape polygonal_light.c creates
+    by default, reference variant ris_ltc_v4): in FAST precision ris_ltc4_kernel + winner_kernel<.., 4> instead of the
+    generic kernel. Same gates as the triangle path: visibility bit-exact, >= 99 % of the pixels at 1 / 4 / 16 spp."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    kw = dict(min_vertices=4, max_vertices=4)
+    scene = scenes.many_light_room(64, 60, seed=7, width=320, height=180, vertex_count=4)
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 320, 180, frames, "fast")
+    assert np.array_equal(vis, ref_vis)
+    check("room 64 quad lights 320x180, default estimator", "fast", got, ref, frames, counters, ref_rays)
+    assert abs(counters["shadow_rays"] - ref_rays) <= max(8, ref_rays // 10000)
+    assert counters["candidates"] == 32 * counters["shaded_pixels"]      # the counters of the specialised RIS kernel
+
+
 @pytest.mark.parametrize("precision", ["exact", "fast"])
 @pytest.mark.parametrize("lights", [1024, 4096])
 def test_many_lights(device, ltc_tables, lights, precision):

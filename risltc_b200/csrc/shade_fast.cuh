@@ -71,6 +71,10 @@ __device__ __noinline__ float ff_clipped_triangle(float3 p0, float3 p1, float3 p
 // warp-uniform registers). Results go to the warp's form-factor table, from which the pixel's lane replays its
 // reservoir in the reference's order.
 #define RL_CHUNK 8            // candidates per pass (four passes cover m = 32)
+// Measured alternatives (round 2, C2, 0.727 ms per frame as is): 16 candidates per pass (half the partially filled drains at
+// the end of a pass, 22 warps) 0.722 ms; the candidate loop unrolled by two (loads of the next candidate under the arithmetic of
+// this one; 8 bytes of spills) 0.736 ms.
+constexpr int kPass1Unroll = 1;
 #define RL_QUEUE 128          // polygons per warp queue: <= 31 + 31 left waiting + <= 64 pushed per candidate
 #define RL_ITEM_WORDS 12      // p0, p1, p2, mask, destination slot, pad: three 16-byte accesses, conflict-free at this stride
 #define RL_WARP_WORDS (2 * RL_CHUNK * 32 + RL_QUEUE * RL_ITEM_WORDS)   // 8 KB per warp
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 			for (int i = 0; i != 2 * RL_CHUNK / 4; ++i) ((float4*) ff)[i * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 			__syncwarp();
 			// pass 1: transform and classify the candidates (target function: LTC integrals, shading_pass.frag.glsl:430-456)
-			#pragma unroll 1
+			#pragma unroll kPass1Unroll
 			for (int j = 0; j != RL_CHUNK; ++j) {
 				// inactive lanes run the same arithmetic on a frame of zeros: their polygons have z = 0 and are never queued
 				seed = 1664525u * seed + 1013904223u;

@@ -93,14 +93,17 @@ int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* var
 int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 
 /* Builder of the acceleration structures (create_acceleration_structure, scene.c:142-406, where the driver builds on the
- * device): HOST = binned SAH on one host thread (best traversal cost, ~1.3 us per triangle), DEVICE = Morton-order radix tree
- * built by kernels (bvh_gpu.cu; 5 M triangles in 15 ms instead of 6.9 s, shadow rays 1.2-1.5x costlier), AUTO (default) =
- * DEVICE from 8 M triangles on. Takes effect at the next upload_scene; images do not depend on it. Environment: RISLTC_BVH_BUILD=host|gpu.
+ * device): HOST = binned SAH on one host thread (~1.5 us per triangle: 7-8 s for 5 M triangles), DEVICE = built by kernels
+ * (bvh_gpu.cu): Morton order + PLOC clustering, 5 M triangles in 24 ms; shadow rays cost -3 .. +9 % against the SAH tree,
+ * the per-pixel BVH walk of huge scenes +40 %; DEVICE_RADIX = the plain radix tree over the Morton order (13 ms, shadow
+ * rays 1.2-1.5x costlier). AUTO (default) = DEVICE from 8 M triangles on. Takes effect at the next upload_scene; images do
+ * not depend on it. Environment: RISLTC_BVH_BUILD=host|gpu|radix, RISLTC_BVH_PLOC_RADIUS=<1..32> (16).
  * bvh_stats: {builder used, wall ms of the build, device ms of sort + hierarchy / boxes + records / 4-wide collapse,
  * binary node slots, 4-wide nodes, binary depth << 16 | 4-wide depth}. */
 #define RISLTC_BVH_BUILDER_HOST 0u
 #define RISLTC_BVH_BUILDER_DEVICE 1u
 #define RISLTC_BVH_BUILDER_AUTO 2u
+#define RISLTC_BVH_BUILDER_DEVICE_RADIX 3u
 int risltc_cuda_set_bvh_builder(risltc_device_t* device, uint32_t builder);
 int risltc_cuda_bvh_stats(risltc_device_t* device, double stats[8]);
 

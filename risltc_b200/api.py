@@ -139,13 +139,13 @@ class Device:
 
     def set_bvh_builder(self, builder="auto"):
         """Builder of the acceleration structures for the next upload_mesh: host (binned SAH), device (Morton-order radix tree) or auto."""
-        _check(lib().risltc_cuda_set_bvh_builder(self.h, C.c_uint32({"host": 0, "device": 1, "auto": 2}[builder])))
+        _check(lib().risltc_cuda_set_bvh_builder(self.h, C.c_uint32({"host": 0, "device": 1, "auto": 2, "radix": 3}[builder])))
 
     def bvh_stats(self):
         out = (C.c_double * 8)()
         _check(lib().risltc_cuda_bvh_stats(self.h, out))
         v = [float(x) for x in out]
-        return dict(builder="device" if v[0] else "host", build_ms=v[1], device_ms=v[2:5], binary_node_slots=int(v[5]), wide_nodes=int(v[6]),
+        return dict(builder={0: "host", 1: "device", 3: "radix"}[int(v[0])], build_ms=v[1], device_ms=v[2:5], binary_node_slots=int(v[5]), wide_nodes=int(v[6]),
                     binary_depth=int(v[7]) >> 16, wide_depth=int(v[7]) & 0xFFFF)
 
     def check_scene_bvh(self):

@@ -30,9 +30,9 @@ int rl_fail(const char* what, const char* detail) {
 
 #define RL_FRAME_EVENTS 6
 // auto: scenes from 8 M triangles on are built on the device. Measured on B200 (gpurun_out/wl_*_bvh_*.json, round 2): 5 M triangles
-// (C4) build in 6.9 s on the host and in 14.5 ms on the device (4.1 ms of kernels), but the Morton-order tree costs +23 % shadow-ray
-// time and +33 % primary-visibility time there (+50 % shadow-ray time on the small scenes C2 / C3): a scene is built once and
-// rendered for thousands of frames, so the host's binned-SAH tree stays the default until its build time reaches ~10 s.
+// (C4) build in 7-8 s on the host and in 24 ms on the device (PLOC; 14.6 ms of kernels). The clustered tree is as good as the
+// SAH tree for shadow rays (C2 -3 %, C3 +3 %, C4 +9 % kernel time) but costs the per-pixel BVH walk of C4 +40 %: a scene is
+// built once and rendered for thousands of frames, so the host's binned-SAH tree stays the default until its build takes ~10 s.
 #define RL_GPU_BUILD_TRIANGLES (1ull << 23)
 
 struct risltc_device_s {
@@ -91,6 +91,7 @@ struct risltc_device_s {
 	// acceleration-structure builder: 0 = host (binned SAH, bvh_build.cpp), 1 = device (Morton-order radix tree, bvh_gpu.cu), 2 = auto:
 	// the device builder from RL_GPU_BUILD_TRIANGLES triangles on, where the host build takes ~10 s (RISLTC_BVH_BUILD=host|gpu)
 	uint32_t bvh_builder = 2;
+	uint32_t ploc_radius = 16;   // device builder: search radius of the clustering (RISLTC_BVH_PLOC_RADIUS; 0 = radix tree over the Morton order)
 	double bvh_stats[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };   // builder used, wall ms of the build, device ms x3, binary node slots, 4-wide nodes, binary depth << 16 | 4-wide depth
 	uint64_t node_count = 0, node4_count = 0;
 	unsigned long long launches = 0;
@@ -159,8 +160,9 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_OVERLAP")) { d->overlap = atoi(e) != 0; d->overlap_pinned = true; }
 	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
+	if (const char* e = getenv("RISLTC_BVH_PLOC_RADIUS")) d->ploc_radius = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_RIS_WARPS")) d->ris_warps = (uint32_t) atoi(e);
-	if (const char* e = getenv("RISLTC_BVH_BUILD")) d->bvh_builder = (strcmp(e, "gpu") == 0 || strcmp(e, "device") == 0) ? 1u : (strcmp(e, "host") == 0) ? 0u : 2u;
+	if (const char* e = getenv("RISLTC_BVH_BUILD")) d->bvh_builder = (strcmp(e, "gpu") == 0 || strcmp(e, "device") == 0) ? 1u : (strcmp(e, "radix") == 0) ? 3u : (strcmp(e, "host") == 0) ? 0u : 2u;
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : (atoi(e) == 4) ? 4u : 8u;
 	*device = d;
 	return 0;
@@ -227,16 +229,16 @@ extern "C" int risltc_cuda_upload_scene(risltc_device_t* d, const uint32_t* quan
 	// acceleration structure
 	uint32_t max_leaf = 2;   // measured best for the 4-wide any-hit kernel (a triangle test costs about as much as three box tests)
 	if (const char* e = getenv("RISLTC_BVH_LEAF")) max_leaf = (uint32_t) atoi(e);
-	const bool on_device = (d->bvh_builder == 1u || (d->bvh_builder == 2u && T >= RL_GPU_BUILD_TRIANGLES)) && T > 16;
+	const bool on_device = (d->bvh_builder == 1u || d->bvh_builder == 3u || (d->bvh_builder == 2u && T >= RL_GPU_BUILD_TRIANGLES)) && T > 16;
 	const auto wall_start = std::chrono::steady_clock::now();
 	for (double& v : d->bvh_stats) v = 0.0;
 	if (on_device) {
 		uint64_t counts[2]; uint32_t depths[2]; float ms[3];
-		if (rl_build_bvh_gpu(d->positions, T, factor, summand, max_leaf, &d->nodes, &d->tris, &d->nodes4, counts, depths, ms)) return 1;
+		if (rl_build_bvh_gpu(d->positions, T, factor, summand, max_leaf, d->bvh_builder == 3u ? 0u : d->ploc_radius, &d->nodes, &d->tris, &d->nodes4, counts, depths, ms)) return 1;
 		if (depths[0] > RL_STACK) return fail("upload_scene: the device-built binary acceleration structure is deeper than the traversal stack (RISLTC_BVH_BUILD=host builds a balanced one)", nullptr);
 		if (3u * depths[1] + 1u > RL_T4_OVERFLOW) return fail("upload_scene: the device-built acceleration structure is deeper than the traversal stack", nullptr);
 		d->node_count = counts[0]; d->node4_count = counts[1];
-		d->bvh_stats[0] = 1.0; d->bvh_stats[2] = ms[0]; d->bvh_stats[3] = ms[1]; d->bvh_stats[4] = ms[2];
+		d->bvh_stats[0] = (d->bvh_builder == 3u || d->ploc_radius == 0u) ? 3.0 : 1.0; d->bvh_stats[2] = ms[0]; d->bvh_stats[3] = ms[1]; d->bvh_stats[4] = ms[2];
 		d->bvh_stats[7] = (double) ((depths[0] << 16) | depths[1]);
 	}
 	else {
@@ -966,7 +968,7 @@ extern "C" int risltc_cuda_check_scene_bvh(risltc_device_t* d, uint64_t report[6
 
 extern "C" int risltc_cuda_set_bvh_builder(risltc_device_t* d, uint32_t builder) {
 	if (use(d)) return 1;
-	if (builder > RISLTC_BVH_BUILDER_AUTO) return fail("set_bvh_builder: unknown builder", nullptr);
+	if (builder > RISLTC_BVH_BUILDER_DEVICE_RADIX) return fail("set_bvh_builder: unknown builder", nullptr);
 	d->bvh_builder = builder;
 	return 0;
 }

@@ -16,6 +16,8 @@
 #define RL_NS gpubuild
 #include "internal.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <vector>
 
 using namespace RL_NS;
@@ -72,11 +74,11 @@ __global__ void tris_kernel(const uint2* positions, const uint32_t* order, uint3
 	r.v0 = make_float4(v0[0], v0[1], v0[2], __uint_as_float(id));
 	r.e1 = make_float4(__fsub_rn(v1[0], v0[0]), __fsub_rn(v1[1], v0[1]), __fsub_rn(v1[2], v0[2]), 0.0f);
 	r.e2 = make_float4(__fsub_rn(v2[0], v0[0]), __fsub_rn(v2[1], v0[1]), __fsub_rn(v2[2], v0[2]), 0.0f);
-	tris[slot] = r;
+	if (tris) tris[slot] = r;
 	Box6 b;
 	#pragma unroll
 	for (int k = 0; k != 3; ++k) { b.lo[k] = fminf(v0[k], fminf(v1[k], v2[k])); b.hi[k] = fmaxf(v0[k], fmaxf(v1[k], v2[k])); }
-	leaf_box[slot] = b;
+	if (leaf_box) leaf_box[slot] = b;
 }
 
 // length of the common prefix of keys i and j (duplicates: continue with the index), -1 outside the array
@@ -186,6 +188,109 @@ __global__ void nodes_kernel(int T, uint32_t max_leaf, float pad, const int2* ch
 	nodes[i] = n;
 }
 
+// ---- PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): bottom-up agglomeration along the Morton curve.
+// Clusters ids: 0 .. T-1 are the triangles in Morton order, T .. 2T-2 the inner nodes in the order they are created (the
+// root last). Every round each cluster looks at its `radius` neighbours on either side for the partner with the smallest
+// merged surface area; mutual choices merge. Trees come out within a few per cent of the binned-SAH builder's traversal cost.
+#define RL_PLOC_BLOCK 256
+#define RL_PLOC_MAX_RADIUS 32
+#define RL_PLOC_NONE 0xFFFFFFFFu
+__device__ __forceinline__ float box_half_area(const Box6& a, const Box6& b) {
+	const float dx = fmaxf(a.hi[0], b.hi[0]) - fminf(a.lo[0], b.lo[0]), dy = fmaxf(a.hi[1], b.hi[1]) - fminf(a.lo[1], b.lo[1]), dz = fmaxf(a.hi[2], b.hi[2]) - fminf(a.lo[2], b.lo[2]);
+	return dx * dy + dy * dz + dz * dx;
+}
+__global__ void __launch_bounds__(RL_PLOC_BLOCK) ploc_neighbour_kernel(const uint32_t* cluster, int n, const Box6* box, int* nearest, int radius) {
+	__shared__ Box6 tile[RL_PLOC_BLOCK + 2 * RL_PLOC_MAX_RADIUS];
+	const int base = (int) (blockIdx.x * RL_PLOC_BLOCK) - radius;
+	for (int k = threadIdx.x; k < RL_PLOC_BLOCK + 2 * radius; k += RL_PLOC_BLOCK) {
+		const int j = base + k;
+		if (j >= 0 && j < n) tile[k] = box[cluster[j]];
+	}
+	__syncthreads();
+	const int i = (int) (blockIdx.x * RL_PLOC_BLOCK + threadIdx.x);
+	if (i >= n) return;
+	const Box6 mine = tile[threadIdx.x + radius];
+	float best = INFINITY; int best_j = -1, best_distance = 0x7FFFFFFF;
+	// candidates in the order: distance 1, 2, ...; at equal distance the side that pairs (0,1), (2,3), ... first, so that equal
+	// costs (coincident geometry) still produce mutual choices and halve the cluster count every round
+	for (int distance = 1; distance <= radius; ++distance) {
+		#pragma unroll
+		for (int side = 0; side != 2; ++side) {
+			const bool forward = ((i & 1) == 0) == (side == 0);
+			const int j = forward ? i + distance : i - distance;
+			if (j < 0 || j >= n) continue;
+			const float area = box_half_area(mine, tile[j - base]);
+			if (area < best || (area == best && distance < best_distance)) { best = area; best_j = j; best_distance = distance; }
+		}
+	}
+	nearest[i] = best_j;
+}
+__global__ void ploc_merge_kernel(const uint32_t* cluster, int n, const int* nearest, Box6* box, int2* kids, int* parent, unsigned int* node_count, uint32_t* out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int j = nearest[i];
+	const uint32_t mine = cluster[i];
+	if (j < 0 || nearest[j] != i) { out[i] = mine; return; }
+	if (i > j) { out[i] = RL_PLOC_NONE; return; }
+	const uint32_t other = cluster[j];
+	const uint32_t id = atomicAdd(node_count, 1u);
+	kids[id] = make_int2((int) mine, (int) other);
+	parent[mine] = (int) id; parent[other] = (int) id;
+	box[id] = merge(box[mine], box[other]);
+	out[i] = id;
+}
+struct IsCluster { __device__ __forceinline__ bool operator()(const uint32_t& c) const { return c != RL_PLOC_NONE; } };
+
+// Leaves of two triangles: an inner node whose children are both triangles becomes one leaf, and its triangles get adjacent
+// slots. unit[s] = slots that triangle s (Morton order) claims at its place of the new order: 2 for the first child of such a
+// node (itself + its sibling), 0 for the second, 1 for a triangle that stays a leaf of its own.
+__global__ void ploc_units_kernel(int T, uint32_t max_leaf, const int* parent, const int2* kids, uint32_t* unit) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= T) return;
+	const int2 k = kids[parent[s]];
+	const bool pair = max_leaf >= 2u && k.x < T && k.y < T;
+	unit[s] = pair ? (s == k.x ? 2u : 0u) : 1u;
+}
+__global__ void ploc_slots_kernel(int T, const uint32_t* unit, const uint32_t* base, const int* parent, const int2* kids, const uint32_t* order, uint32_t* new_slot, uint32_t* new_order) {
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= T) return;
+	const uint32_t slot = (unit[s] == 0u) ? base[kids[parent[s]].x] + 1u : base[s];
+	new_slot[s] = slot;
+	new_order[slot] = order[s];
+}
+// BvhNode records; inner id -> index (last - id), so that the root (created last) is node 0
+__global__ void ploc_nodes_kernel(int T, int last, uint32_t max_leaf, float pad, const int2* kids, const Box6* box, const uint32_t* new_slot, BvhNode* nodes) {
+	const int id = T + blockIdx.x * blockDim.x + threadIdx.x;
+	if (id > last) return;
+	const int2 k = kids[id];
+	if (max_leaf >= 2u && k.x < T && k.y < T && id != last) return;   // a two-triangle leaf: referenced as a leaf by its parent
+	int ref[2];
+	#pragma unroll
+	for (int side = 0; side != 2; ++side) {
+		const int c = side ? k.y : k.x;
+		if (c < T) ref[side] = ~(int) ((new_slot[c] << 4) | 0u);
+		else {
+			const int2 g = kids[c];
+			ref[side] = (max_leaf >= 2u && g.x < T && g.y < T) ? ~(int) ((new_slot[g.x] << 4) | 1u) : last - c;
+		}
+	}
+	const Box6 l = box[k.x], r = box[k.y];
+	BvhNode n;
+	n.a = make_float4(l.lo[0] - pad, l.lo[1] - pad, l.lo[2] - pad, l.hi[0] + pad);
+	n.b = make_float4(l.hi[1] + pad, l.hi[2] + pad, r.lo[0] - pad, r.lo[1] - pad);
+	n.c = make_float4(r.lo[2] - pad, r.hi[0] + pad, r.hi[1] + pad, r.hi[2] + pad);
+	n.d = make_int4(ref[0], ref[1], 0, 0);
+	nodes[last - id] = n;
+}
+__global__ void ploc_depth_kernel(int T, const int* parent, unsigned int* depth) {
+	const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+	if (leaf >= T) return;
+	unsigned int levels = 0;
+	for (int node = parent[leaf]; node >= 0; node = parent[node]) ++levels;
+	levels = __reduce_max_sync(__activemask(), levels);
+	if ((threadIdx.x & 31u) == 0u) atomicMax(depth, levels);
+}
+
 // ---- 4-wide collapse, one level per launch
 struct Child4 { int ref; float lo[3], hi[3]; };
 __device__ __forceinline__ float half_area(const Child4& c) {
@@ -268,14 +373,23 @@ __global__ void collapse_kernel(const BvhNode* binary, const WideItem* in, uint3
 template <class T> struct Scratch {
 	T* p = nullptr;
 	cudaError_t alloc(size_t n) { return cudaMalloc(&p, sizeof(T) * (n ? n : 1)); }
+	T* release() { T* r = p; p = nullptr; return r; }
 	~Scratch() { cudaFree(p); }
+};
+struct Events {
+	cudaEvent_t e[4] = { nullptr, nullptr, nullptr, nullptr };
+	cudaError_t create() { for (auto& x : e) { cudaError_t r = cudaEventCreate(&x); if (r != cudaSuccess) return r; } return cudaSuccess; }
+	~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
 };
 
 }  // namespace
 
 // Builds the three arrays of SceneView from the quantised positions already on the device. On success the caller owns
 // *nodes, *tris, *nodes4 (cudaFree). ms[0..2] = sort + hierarchy, boxes + records, 4-wide collapse (device time).
-int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const float factor[3], const float summand[3], uint32_t max_leaf,
+__global__ void iota_kernel(uint32_t* v, int n) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = (uint32_t) i; }
+
+// ploc_radius: 0 = Karras' radix tree over the Morton order (fastest build), 1..32 = PLOC with that search radius
+int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const float factor[3], const float summand[3], uint32_t max_leaf, uint32_t ploc_radius,
 	BvhNode** nodes, BvhTri** tris, Qbvh4Node** nodes4, uint64_t counts[2], uint32_t depths[2], float ms[3])
 {
 	const int T = (int) triangle_count;
@@ -286,8 +400,9 @@ int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const floa
 	float extent = 0.0f;
 	for (int k = 0; k != 3; ++k) { dq.factor[k] = factor[k]; dq.summand[k] = summand[k]; extent = fmaxf(extent, fabsf(factor[k]) * 2097151.0f); }
 	const float pad = 1.0e-5f * extent + 1.0e-7f;
-	cudaEvent_t ev[4];
-	for (auto& e : ev) CU(cudaEventCreate(&e));
+	Events events;   // everything allocated here is released on every return path (Scratch / Events destructors)
+	CU(events.create());
+	cudaEvent_t* ev = events.e;
 	Scratch<unsigned long long> keys, keys_sorted; Scratch<uint32_t> values, order; Scratch<unsigned char> temp;
 	Scratch<int2> children, range; Scratch<int> inner_parent, leaf_parent; Scratch<Box6> leaf_box, node_box; Scratch<unsigned int> arrived, scalars;
 	Scratch<WideItem> frontier[2];
@@ -295,9 +410,10 @@ int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const floa
 	CU(children.alloc(T)); CU(range.alloc(T)); CU(inner_parent.alloc(T)); CU(leaf_parent.alloc(T)); CU(leaf_box.alloc(T)); CU(node_box.alloc(T));
 	CU(arrived.alloc(T)); CU(scalars.alloc(4));
 	CU(cudaMemset(arrived.p, 0, sizeof(unsigned int) * T)); CU(cudaMemset(scalars.p, 0, 4 * sizeof(unsigned int)));
-	BvhNode* out_nodes = nullptr; BvhTri* out_tris = nullptr; Qbvh4Node* wide = nullptr;
-	CU(cudaMalloc(&out_nodes, sizeof(BvhNode) * (size_t) (T - 1)));
-	CU(cudaMalloc(&out_tris, sizeof(BvhTri) * (size_t) T));
+	Scratch<BvhNode> nodes_out; Scratch<BvhTri> tris_out; Scratch<Qbvh4Node> wide_all, wide_compact;
+	CU(nodes_out.alloc((size_t) (T - 1)));
+	CU(tris_out.alloc((size_t) T));
+	BvhNode* const out_nodes = nodes_out.p; BvhTri* const out_tris = tris_out.p;
 	CU(cudaMemset(out_nodes, 0, sizeof(BvhNode) * (size_t) (T - 1)));   // slots of nodes inside leaves stay unreferenced
 	const int block = 256, grid = (T + block - 1) / block;
 	CU(cudaEventRecord(ev[0]));
@@ -306,15 +422,59 @@ int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const floa
 	CU(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys.p, keys_sorted.p, values.p, order.p, T, 0, 63));
 	CU(temp.alloc(temp_bytes));
 	CU(cub::DeviceRadixSort::SortPairs(temp.p, temp_bytes, keys.p, keys_sorted.p, values.p, order.p, T, 0, 63));
-	hierarchy_kernel<<<grid, block>>>(keys_sorted.p, T, children.p, range.p, inner_parent.p, leaf_parent.p);
-	CU(cudaEventRecord(ev[1]));
-	tris_kernel<<<grid, block>>>(positions, order.p, (uint32_t) T, dq, out_tris, leaf_box.p);
-	boxes_kernel<<<grid, block>>>(T, children.p, inner_parent.p, leaf_parent.p, leaf_box.p, node_box.p, arrived.p);
-	depth_kernel<<<grid, block>>>(T, inner_parent.p, leaf_parent.p, scalars.p);
-	nodes_kernel<<<grid, block>>>(T, max_leaf, pad, children.p, range.p, leaf_box.p, node_box.p, out_nodes);
-	CU(cudaEventRecord(ev[2]));
+	if (ploc_radius > RL_PLOC_MAX_RADIUS) ploc_radius = RL_PLOC_MAX_RADIUS;
+	if (T < 4) ploc_radius = 0;
+	if (ploc_radius) {
+		Scratch<Box6> box; Scratch<int2> kids; Scratch<int> parent, nearest; Scratch<uint32_t> cluster[2], unit, base, new_slot, new_order; Scratch<unsigned char> temp2;
+		CU(box.alloc(2 * (size_t) T)); CU(kids.alloc(2 * (size_t) T)); CU(parent.alloc(2 * (size_t) T)); CU(nearest.alloc(T));
+		CU(cluster[0].alloc(T)); CU(cluster[1].alloc(T)); CU(unit.alloc(T)); CU(base.alloc(T)); CU(new_slot.alloc(T)); CU(new_order.alloc(T));
+		size_t select_bytes = 0, scan_bytes = 0;
+		CU(cub::DeviceSelect::If(nullptr, select_bytes, cluster[0].p, cluster[1].p, scalars.p + 1, T, IsCluster()));
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, unit.p, base.p, T));
+		CU(temp2.alloc(select_bytes > scan_bytes ? select_bytes : scan_bytes));
+		size_t temp2_bytes = select_bytes > scan_bytes ? select_bytes : scan_bytes;
+		tris_kernel<<<grid, block>>>(positions, order.p, (uint32_t) T, dq, nullptr, box.p);      // boxes of the triangles in Morton order
+		iota_kernel<<<grid, block>>>(cluster[0].p, T);
+		const unsigned int first_inner = (unsigned int) T;
+		CU(cudaMemcpy(scalars.p + 3, &first_inner, sizeof(first_inner), cudaMemcpyHostToDevice));   // scalars[3]: next node id
+		int n = T, rounds = 0, side = 0;
+		while (n > 1) {
+			const int g = (n + RL_PLOC_BLOCK - 1) / RL_PLOC_BLOCK;
+			ploc_neighbour_kernel<<<g, RL_PLOC_BLOCK>>>(cluster[side].p, n, box.p, nearest.p, (int) ploc_radius);
+			ploc_merge_kernel<<<g, RL_PLOC_BLOCK>>>(cluster[side].p, n, nearest.p, box.p, kids.p, parent.p, scalars.p + 3, cluster[side ^ 1].p);
+			// compact the survivors and the new nodes in place of their left members (the order along the curve is kept)
+			CU(cub::DeviceSelect::If(temp2.p, temp2_bytes, cluster[side ^ 1].p, cluster[side].p, scalars.p + 1, n, IsCluster()));
+			unsigned int survivors = 0;
+			CU(cudaMemcpy(&survivors, scalars.p + 1, sizeof(survivors), cudaMemcpyDeviceToHost));
+			if ((int) survivors >= n || survivors == 0u) return rl_fail("build_bvh_gpu: clustering made no progress", nullptr);
+			n = (int) survivors;
+			if (++rounds > 4096) return rl_fail("build_bvh_gpu: clustering does not terminate", nullptr);
+		}
+		const int last = 2 * T - 2;   // the root: T - 1 inner nodes were created, the last one by the final merge
+		const int no_parent = -1;
+		CU(cudaMemcpy(parent.p + last, &no_parent, sizeof(int), cudaMemcpyHostToDevice));
+		CU(cudaEventRecord(ev[1]));
+		ploc_units_kernel<<<grid, block>>>(T, max_leaf, parent.p, kids.p, unit.p);
+		CU(cub::DeviceScan::ExclusiveSum(temp2.p, temp2_bytes, unit.p, base.p, T));
+		ploc_slots_kernel<<<grid, block>>>(T, unit.p, base.p, parent.p, kids.p, order.p, new_slot.p, new_order.p);
+		tris_kernel<<<grid, block>>>(positions, new_order.p, (uint32_t) T, dq, out_tris, nullptr);
+		ploc_nodes_kernel<<<(T - 1 + block - 1) / block, block>>>(T, last, max_leaf, pad, kids.p, box.p, new_slot.p, out_nodes);
+		ploc_depth_kernel<<<grid, block>>>(T, parent.p, scalars.p);
+		CU(cudaEventRecord(ev[2]));
+		CU(cudaDeviceSynchronize());   // the scratch arrays of this block are freed when it ends
+	}
+	else {
+		hierarchy_kernel<<<grid, block>>>(keys_sorted.p, T, children.p, range.p, inner_parent.p, leaf_parent.p);
+		CU(cudaEventRecord(ev[1]));
+		tris_kernel<<<grid, block>>>(positions, order.p, (uint32_t) T, dq, out_tris, leaf_box.p);
+		boxes_kernel<<<grid, block>>>(T, children.p, inner_parent.p, leaf_parent.p, leaf_box.p, node_box.p, arrived.p);
+		depth_kernel<<<grid, block>>>(T, inner_parent.p, leaf_parent.p, scalars.p);
+		nodes_kernel<<<grid, block>>>(T, max_leaf, pad, children.p, range.p, leaf_box.p, node_box.p, out_nodes);
+		CU(cudaEventRecord(ev[2]));
+	}
 	// 4-wide collapse: frontier of (binary node, output slot), one launch per level
-	CU(cudaMalloc(&wide, sizeof(Qbvh4Node) * (size_t) T));
+	CU(wide_all.alloc((size_t) T));
+	Qbvh4Node* const wide = wide_all.p;
 	CU(frontier[0].alloc(T)); CU(frontier[1].alloc(T));
 	const WideItem root = { 0, 0u };
 	CU(cudaMemcpy(frontier[0].p, &root, sizeof(root), cudaMemcpyHostToDevice));
@@ -334,13 +494,10 @@ int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const floa
 	unsigned int host_scalars[4];
 	CU(cudaMemcpy(host_scalars, scalars.p, sizeof(host_scalars), cudaMemcpyDeviceToHost));
 	// shrink the 4-wide array to its size
-	Qbvh4Node* compact = nullptr;
-	CU(cudaMalloc(&compact, sizeof(Qbvh4Node) * (size_t) host_scalars[2]));
-	CU(cudaMemcpy(compact, wide, sizeof(Qbvh4Node) * (size_t) host_scalars[2], cudaMemcpyDeviceToDevice));
-	cudaFree(wide);
+	CU(wide_compact.alloc((size_t) host_scalars[2]));
+	CU(cudaMemcpy(wide_compact.p, wide, sizeof(Qbvh4Node) * (size_t) host_scalars[2], cudaMemcpyDeviceToDevice));
 	for (int i = 0; i != 3; ++i) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
-	for (auto& e : ev) cudaEventDestroy(e);
-	*nodes = out_nodes; *tris = out_tris; *nodes4 = compact;
+	*nodes = nodes_out.release(); *tris = tris_out.release(); *nodes4 = wide_compact.release();
 	counts[0] = (uint64_t) (T - 1); counts[1] = host_scalars[2];
 	depths[0] = host_scalars[0]; depths[1] = levels;
 	return 0;

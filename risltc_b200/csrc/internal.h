@@ -23,5 +23,5 @@ int rl_launch_winner_cr(const SceneView& s, const FrameUniforms& f, const Stripe
 
 // bvh_gpu.cu: the acceleration structures of upload_scene built on the device from the quantised positions already there.
 // counts = {binary node slots, 4-wide nodes}, depths = {binary levels, 4-wide levels}, ms = {sort + hierarchy, boxes + records, collapse}
-int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const float factor[3], const float summand[3], uint32_t max_leaf,
+int rl_build_bvh_gpu(const uint2* positions, uint64_t triangle_count, const float factor[3], const float summand[3], uint32_t max_leaf, uint32_t ploc_radius,
 	BvhNode** nodes, BvhTri** tris, Qbvh4Node** nodes4, uint64_t counts[2], uint32_t depths[2], float ms[3]);

@@ -267,7 +267,7 @@ def test_device_built_acceleration_structure(device, ltc_tables):
     want = np.array([osc.any_hit(r[0:3], r[4:7], float(r[3]), float(r[7])) for r in rays], dtype=np.uint32)
     results = {}
     try:
-        for builder in ("host", "device"):
+        for builder in ("host", "device", "radix"):
             device.set_bvh_builder(builder)
             setup_device(device, scene, rgba, rg, api.variant(), W, H, osc.records)
             stats, report = device.bvh_stats(), device.check_scene_bvh()

@@ -66,7 +66,7 @@ struct risltc_device_s {
 	uint32_t precision = RISLTC_PRECISION_FAST;
 	int sm_count = 148, trace_resident = 1, trace4_resident = 1, trace4p_resident = 1;
 	int trace_ctas_per_sm = 0;   // 0: as many as fit
-	uint32_t refill = RL_TRACE_REFILL;   // idle lanes that trigger a refill of the warp from its staged rays
+	uint32_t refill = 4;   // idle lanes that trigger a refill of the warp from its staged rays (sweep with the pair kernel, round 2: 1 / 2 / 4 / 6 / 10 -> C2 trace -- / 10.19 / 10.08 / 10.18 / 10.49 ms, C3 231.4 / 226.8 / 226.8 / 229.7 / 239.2 ms; RISLTC_REFILL)
 	// (1) has two bit-identical implementations: 1 = triangle-parallel rasteriser (raster.cuh; wins when few triangles cover
 	// the screen), 0 = per-pixel BVH walk (gbuffer_kernel; wins at high depth complexity). Unless RISLTC_GBUFFER pins one, the
 	// first two frames after a scene upload / resize run one each, timed with events, and the faster one is kept.

@@ -16,7 +16,9 @@ timeout 1200 python bench.py --workload c5 --steps 3 --warmup 2 --no-cpu-baselin
 for est in uniform_uniform uniform_cp uniform_area cp_cp; do
   timeout 600 python bench.py --estimator $est --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/est_$est.json 2> gpurun_out/est_$est.err
 done
-RISLTC_OVERLAP=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_overlap1.json 2> gpurun_out/bench_overlap1.err
+timeout 600 python bench.py --textured --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_textured.json 2> gpurun_out/bench_textured.err
+timeout 600 python bench.py --light-vertices 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quads.json 2> gpurun_out/bench_quads.err
+RISLTC_OVERLAP=0 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_overlap0.json 2> gpurun_out/bench_overlap0.err
 # under the profiler the timed choice between the two visibility implementations is distorted by the per-kernel overhead: pin what the un-profiled bench chooses on C2
 export RISLTC_GBUFFER=raster
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
@@ -27,7 +29,7 @@ unset RISLTC_GBUFFER
 tail -n 3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.err
 python - <<'P'
 import json, glob
-for f in sorted(glob.glob('gpurun_out/bench.json') + glob.glob('gpurun_out/wl_c[1-4].json') + glob.glob('gpurun_out/est_*.json') + glob.glob('gpurun_out/bench_overlap1.json') + glob.glob('gpurun_out/bench_reference.json')):
+for f in sorted(glob.glob('gpurun_out/bench.json') + glob.glob('gpurun_out/wl_c[1-4].json') + glob.glob('gpurun_out/est_*.json') + glob.glob('gpurun_out/bench_overlap0.json') + glob.glob('gpurun_out/bench_textured.json') + glob.glob('gpurun_out/bench_quads.json') + glob.glob('gpurun_out/bench_reference.json')):
     try:
         j = json.loads(open(f).read().strip().splitlines()[-1])
         print(f, round(j['value'], 3), 'e2e', round(j['e2e']['value'], 3), 'frac', j.get('roofline', {}).get('frac'), {k: round(v, 3) for k, v in j.get('kernels', {}).items() if k.endswith('_ms')})

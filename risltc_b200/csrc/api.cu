@@ -29,6 +29,8 @@ int rl_fail(const char* what, const char* detail) {
 #define fail rl_fail
 
 #define RL_FRAME_EVENTS 6
+#define RL_TRACE_CANDIDATES 3u
+#define RL_TRACE_DECIDED (RL_TRACE_CANDIDATES + 1u)
 // auto: scenes from 8 M triangles on are built on the device. Measured on B200 (gpurun_out/wl_*_bvh_*.json, round 2): 5 M triangles
 // (C4) build in 7-8 s on the host and in 24 ms on the device (PLOC; 14.6 ms of kernels). The clustered tree is as good as the
 // SAH tree for shadow rays (C2 -3 %, C3 +3 %, C4 +9 % kernel time) but costs the per-pixel BVH walk of C4 +40 %: a scene is
@@ -85,9 +87,11 @@ struct risltc_device_s {
 	// (1) ends them ~10 % of their node visits earlier. Unless RISLTC_TRI_VOTE pins it, the first two frames after a scene
 	// upload run one candidate each, timed with events, and the faster is kept (the image does not depend on it).
 	uint32_t tri_vote = 8;
-	uint32_t trace_tune = 0;      // 0, 1: time candidate 0 / 1 next, 2: both in flight, 3: decided
+	// ... and, for the pair kernel, whether hit children are visited nearest first (trace4.cuh). RL_TRACE_CANDIDATES settings are timed.
+	bool trace_ordered = true;
+	uint32_t trace_tune = 0;      // 0 .. RL_TRACE_CANDIDATES - 1: time that candidate next, RL_TRACE_CANDIDATES: all in flight, RL_TRACE_DECIDED: decided
 	bool trace_pinned = false;
-	cudaEvent_t trace_tune_ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t trace_tune_ev[2 * RL_TRACE_CANDIDATES] = {};
 	// acceleration-structure builder: 0 = host (binned SAH, bvh_build.cpp), 1 = device (Morton-order radix tree, bvh_gpu.cu), 2 = auto:
 	// the device builder from RL_GPU_BUILD_TRIANGLES triangles on, where the host build takes ~10 s (RISLTC_BVH_BUILD=host|gpu)
 	uint32_t bvh_builder = 2;
@@ -151,7 +155,8 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4p_resident, trace4p_kernel<false>, 128, 0));
-	if (const char* e = getenv("RISLTC_TRI_VOTE")) { d->tri_vote = (uint32_t) atoi(e); d->trace_pinned = true; d->trace_tune = 3u; }   // tuning knobs
+	if (const char* e = getenv("RISLTC_TRI_VOTE")) { d->tri_vote = (uint32_t) atoi(e); d->trace_pinned = true; d->trace_tune = RL_TRACE_DECIDED; }   // tuning knobs
+	if (const char* e = getenv("RISLTC_TRACE_ORDERED")) { d->trace_ordered = atoi(e) != 0; d->trace_pinned = true; d->trace_tune = RL_TRACE_DECIDED; }
 	for (auto& ev : d->trace_tune_ev) CU(cudaEventCreate(&ev));
 	if (const char* e = getenv("RISLTC_WIN_THREADS")) { int t = atoi(e); d->winner_threads = (t == 256 || t == 320) ? (uint32_t) t : 384u; }
 	if (const char* e = getenv("RISLTC_WINNER")) d->winner_cr = strcmp(e, "cr") == 0;
@@ -647,7 +652,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		unpack_constants(f, (const unsigned char*) blocks + 256 * (size_t) i, first_accum_num + i);
 		if (f.width != d->width || f.height != d->height) return fail("render_frames: viewport in the constants differs from resize()", nullptr);
 		// while the G-buffer implementations are being timed the frames stay on one stream; afterwards they alternate
-		const uint32_t set = (overlap && d->gbuffer_tune == 3 && d->trace_tune == 3) ? (alternate++ & 1u) : 0u;
+		const uint32_t set = (overlap && d->gbuffer_tune == 3 && d->trace_tune == RL_TRACE_DECIDED) ? (alternate++ & 1u) : 0u;
 		const PixelBuffers& px = set ? d->px2 : d->px;
 		const RasterBuffers& raster = set ? d->raster2 : d->raster;
 		cudaStream_t stream = set ? d->stream2 : d->stream;
@@ -687,23 +692,31 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
 			const int resident = (d->trace_kind == 8) ? d->trace4p_resident : d->trace4_resident;
 			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < resident) ? d->trace_ctas_per_sm : resident;
-			static const uint32_t vote_candidates[2] = { 8u, 1u };
-			if (d->trace_tune == 2) {
-				float ms[2] = { 0.0f, 0.0f };
-				CU(cudaEventSynchronize(d->trace_tune_ev[3]));
-				CU(cudaEventElapsedTime(&ms[0], d->trace_tune_ev[0], d->trace_tune_ev[1]));
-				CU(cudaEventElapsedTime(&ms[1], d->trace_tune_ev[2], d->trace_tune_ev[3]));
-				d->tri_vote = vote_candidates[(ms[1] < 0.97f * ms[0]) ? 1 : 0];
-				d->trace_tune = 3;
+			// candidates: {triangle-track threshold, nearest child first}; the first is the default and wins ties (3 %)
+			static const uint32_t vote_candidates[RL_TRACE_CANDIDATES] = { 8u, 1u, 8u };
+			static const bool order_candidates[RL_TRACE_CANDIDATES] = { true, true, false };
+			if (d->trace_tune == RL_TRACE_CANDIDATES) {
+				CU(cudaEventSynchronize(d->trace_tune_ev[2 * RL_TRACE_CANDIDATES - 1]));
+				float best_ms = 0.0f; uint32_t best = 0;
+				for (uint32_t c = 0; c != RL_TRACE_CANDIDATES; ++c) {
+					float ms = 0.0f;
+					CU(cudaEventElapsedTime(&ms, d->trace_tune_ev[2 * c], d->trace_tune_ev[2 * c + 1]));
+					if (c == 0 || ms < 0.97f * best_ms) { best_ms = ms; best = c; }
+				}
+				d->tri_vote = vote_candidates[best]; d->trace_ordered = order_candidates[best];
+				d->trace_tune = RL_TRACE_DECIDED;
 			}
 			const uint32_t tuning = d->trace_tune;
-			if (tuning < 2) { d->tri_vote = vote_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
-			if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
-			else if (d->trace_kind == 8) trace4p_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			if (tuning < RL_TRACE_CANDIDATES) { d->tri_vote = vote_candidates[tuning]; d->trace_ordered = order_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
+			const bool ordered = d->trace_ordered || d->trace_kind != 8;
+			if (d->trace_kind == 8 && d->count_traversal && ordered) trace4p_kernel<true, true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true, false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 8 && ordered) trace4p_kernel<false, true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
+			else if (d->trace_kind == 8) trace4p_kernel<false, false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
-			if (tuning < 2) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
+			if (tuning < RL_TRACE_CANDIDATES) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
 			d->launches += 1;
 		}
 		CU(cudaEventRecord(fe[4], stream));

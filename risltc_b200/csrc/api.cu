@@ -30,7 +30,8 @@ int rl_fail(const char* what, const char* detail) {
 
 #define RL_FRAME_EVENTS 6
 #define RL_TRACE_CANDIDATES 3u
-#define RL_TRACE_DECIDED (RL_TRACE_CANDIDATES + 1u)
+#define RL_TRACE_TRIALS (2u * RL_TRACE_CANDIDATES)   // every candidate is timed on two frames (the faster counts: the first frames after an upload run on cold caches)
+#define RL_TRACE_DECIDED (RL_TRACE_TRIALS + 1u)
 // auto: scenes from 8 M triangles on are built on the device. Measured on B200 (gpurun_out/wl_*_bvh_*.json, round 2): 5 M triangles
 // (C4) build in 7-8 s on the host and in 24 ms on the device (PLOC; 14.6 ms of kernels). The clustered tree is as good as the
 // SAH tree for shadow rays (C2 -3 %, C3 +3 %, C4 +9 % kernel time) but costs the per-pixel BVH walk of C4 +40 %: a scene is
@@ -51,7 +52,7 @@ struct risltc_device_s {
 	// variant + targets
 	Variant variant = { 1, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1, 1, 0, 3, 3 };
 	uint32_t width = 0, height = 0;
-	Stripes stripes = { 8, 0, 1, 0 };
+	Stripes stripes = { 8, 0, 1, 0, 3 };
 	PixelBuffers px = {};
 	float4* own_accum = nullptr;
 	uint32_t ray_slots = 0, group_slots = 0;
@@ -89,9 +90,9 @@ struct risltc_device_s {
 	uint32_t tri_vote = 8;
 	// ... and, for the pair kernel, whether hit children are visited nearest first (trace4.cuh). RL_TRACE_CANDIDATES settings are timed.
 	bool trace_ordered = true;
-	uint32_t trace_tune = 0;      // 0 .. RL_TRACE_CANDIDATES - 1: time that candidate next, RL_TRACE_CANDIDATES: all in flight, RL_TRACE_DECIDED: decided
+	uint32_t trace_tune = 0;      // 0 .. RL_TRACE_TRIALS - 1: time candidate (trace_tune % RL_TRACE_CANDIDATES) next, RL_TRACE_TRIALS: all in flight, RL_TRACE_DECIDED: decided
 	bool trace_pinned = false;
-	cudaEvent_t trace_tune_ev[2 * RL_TRACE_CANDIDATES] = {};
+	cudaEvent_t trace_tune_ev[2 * RL_TRACE_TRIALS] = {};
 	// acceleration-structure builder: 0 = host (binned SAH, bvh_build.cpp), 1 = device (Morton-order radix tree, bvh_gpu.cu), 2 = auto:
 	// the device builder from RL_GPU_BUILD_TRIANGLES triangles on, where the host build takes ~10 s (RISLTC_BVH_BUILD=host|gpu)
 	uint32_t bvh_builder = 2;
@@ -519,6 +520,8 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 		owned += (y0 + stripe_height <= height) ? stripe_height : height - y0;
 	d->width = width; d->height = height;
 	d->stripes.stripe_h = stripe_height; d->stripes.stripe_index = stripe_index; d->stripes.stripe_count = stripe_count; d->stripes.owned_rows = owned;
+	d->stripes.h_shift = 0xFFFFFFFFu;
+	for (uint32_t k = 0; k != 32u; ++k) if (stripe_height == (1u << k)) d->stripes.h_shift = k;
 	size_t pixels = (size_t) owned * width;
 	d->px.pixel_count = (uint32_t) pixels;
 	if (pixels == 0) return 0;
@@ -695,19 +698,21 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			// candidates: {triangle-track threshold, nearest child first}; the first is the default and wins ties (3 %)
 			static const uint32_t vote_candidates[RL_TRACE_CANDIDATES] = { 8u, 1u, 8u };
 			static const bool order_candidates[RL_TRACE_CANDIDATES] = { true, true, false };
-			if (d->trace_tune == RL_TRACE_CANDIDATES) {
-				CU(cudaEventSynchronize(d->trace_tune_ev[2 * RL_TRACE_CANDIDATES - 1]));
+			if (d->trace_tune == RL_TRACE_TRIALS) {
+				CU(cudaEventSynchronize(d->trace_tune_ev[2 * RL_TRACE_TRIALS - 1]));
 				float best_ms = 0.0f; uint32_t best = 0;
 				for (uint32_t c = 0; c != RL_TRACE_CANDIDATES; ++c) {
-					float ms = 0.0f;
-					CU(cudaEventElapsedTime(&ms, d->trace_tune_ev[2 * c], d->trace_tune_ev[2 * c + 1]));
+					float first = 0.0f, second = 0.0f;
+					CU(cudaEventElapsedTime(&first, d->trace_tune_ev[2 * c], d->trace_tune_ev[2 * c + 1]));
+					CU(cudaEventElapsedTime(&second, d->trace_tune_ev[2 * (c + RL_TRACE_CANDIDATES)], d->trace_tune_ev[2 * (c + RL_TRACE_CANDIDATES) + 1]));
+					const float ms = std::min(first, second);
 					if (c == 0 || ms < 0.97f * best_ms) { best_ms = ms; best = c; }
 				}
 				d->tri_vote = vote_candidates[best]; d->trace_ordered = order_candidates[best];
 				d->trace_tune = RL_TRACE_DECIDED;
 			}
 			const uint32_t tuning = d->trace_tune;
-			if (tuning < RL_TRACE_CANDIDATES) { d->tri_vote = vote_candidates[tuning]; d->trace_ordered = order_candidates[tuning]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
+			if (tuning < RL_TRACE_TRIALS) { d->tri_vote = vote_candidates[tuning % RL_TRACE_CANDIDATES]; d->trace_ordered = order_candidates[tuning % RL_TRACE_CANDIDATES]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
 			const bool ordered = d->trace_ordered || d->trace_kind != 8;
 			if (d->trace_kind == 8 && d->count_traversal && ordered) trace4p_kernel<true, true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true, false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
@@ -716,7 +721,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			else if (d->trace_kind == 4 && d->count_traversal) trace4_kernel<true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 4) trace4_kernel<false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote, d->refill, 0x3F800000u);
 			else trace_kernel<<<d->sm_count * d->trace_resident, 128, 0, stream>>>(d->view, px, ray_count, d->tri_vote);
-			if (tuning < RL_TRACE_CANDIDATES) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
+			if (tuning < RL_TRACE_TRIALS) { CU(cudaEventRecord(d->trace_tune_ev[2 * tuning + 1], stream)); d->trace_tune = tuning + 1; }
 			d->launches += 1;
 		}
 		CU(cudaEventRecord(fe[4], stream));

@@ -243,7 +243,12 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 			}
 			const uint32_t local = unit - it.first_unit;
 			// tiles are RL_RASTER_TILE pixels wide and RL_RASTER_TILE of this device's LOCAL rows high
-			const uint32_t tile_x = (it.tx0 + local % it.ntx) * RL_RASTER_TILE, tile_row = (it.ty0 + local / it.ntx) * RL_RASTER_TILE;
+			// local / ntx without an integer division (5.6 % of the kernel's instructions): local < 2^20 and ntx <= 2^10, so the
+			// product with the approximate reciprocal is off by < 2.5e-4 while (local + 0.5) / ntx stays 0.5 / ntx >= 4.9e-4 away from an integer
+			// (images beyond 32 k pixels in either direction take the division)
+			const uint32_t tile_j = (it.ntx <= 1024u && it.nty <= 1024u) ? (uint32_t) (((float) local + 0.5f) * approx_rcp((float) it.ntx)) : local / it.ntx;
+			const uint32_t tile_i = local - tile_j * it.ntx;
+			const uint32_t tile_x = (it.tx0 + tile_i) * RL_RASTER_TILE, tile_row = (it.ty0 + tile_j) * RL_RASTER_TILE;
 			const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f;
 			const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + RL_RASTER_TILE, st.owned_rows) - 1u);
 			if (rect_rejected(ef, (float) tile_x, ty0, tx1, ty1)) continue;

@@ -79,6 +79,7 @@ struct risltc_device_s {
 	bool gbuffer_pinned = false;
 	RasterBuffers raster = {};
 	bool winner_cr = false;          // winner_cr.cu: correctly rounded transcendental functions in the winner's estimator (RISLTC_WINNER=cr)
+	uint32_t raster_tile_shift = 0;  // RISLTC_RASTER_TILE_SHIFT=5..8: log2 of the rasteriser's unit width (tuning knob; 0 = by share)
 	uint32_t ris_warps = 0;          // RISLTC_RIS_WARPS=<n>: cap on the warps of the RIS kernel's one CTA per SM (tuning knob; 0 = all that fit, <= 24)
 	uint32_t winner_threads = 384;   // CTA size of the phase-synchronous winner kernel, two CTAs per SM: 384 (80 registers), 320 (96) or 256 (128)
 	bool count_traversal = false; // trace4_kernel<true>: node visits and triangle tests are counted (risltc_cuda_traversal_counters)
@@ -167,6 +168,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	if (const char* e = getenv("RISLTC_TRACE_CTAS")) d->trace_ctas_per_sm = atoi(e);
 	if (const char* e = getenv("RISLTC_REFILL")) d->refill = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_BVH_PLOC_RADIUS")) d->ploc_radius = (uint32_t) atoi(e);
+	if (const char* e = getenv("RISLTC_RASTER_TILE_SHIFT")) { const int v = atoi(e); d->raster_tile_shift = (v >= 5 && v <= 8) ? (uint32_t) v : 0u; }
 	if (const char* e = getenv("RISLTC_RIS_WARPS")) d->ris_warps = (uint32_t) atoi(e);
 	if (const char* e = getenv("RISLTC_BVH_BUILD")) d->bvh_builder = (strcmp(e, "gpu") == 0 || strcmp(e, "device") == 0) ? 1u : (strcmp(e, "radix") == 0) ? 3u : (strcmp(e, "host") == 0) ? 0u : 2u;
 	if (const char* e = getenv("RISLTC_TRACE")) d->trace_kind = (atoi(e) == 2) ? 2u : (atoi(e) == 4) ? 4u : 8u;
@@ -462,6 +464,7 @@ static int ensure_second_set(risltc_device_t* d) {
 	CU(cudaMalloc(&d->raster2.counter, 16));
 	CU(cudaMemset(d->raster2.counter, 0, 16));
 	d->raster2.ticket = (unsigned int*) (d->raster2.counter + 1);
+	d->raster2.tile_shift_x = d->raster.tile_shift_x;
 	d->set2_ready = true;
 	return 0;
 }
@@ -520,6 +523,8 @@ extern "C" int risltc_cuda_resize(risltc_device_t* d, uint32_t width, uint32_t h
 		owned += (y0 + stripe_height <= height) ? stripe_height : height - y0;
 	d->width = width; d->height = height;
 	d->stripes.stripe_h = stripe_height; d->stripes.stripe_index = stripe_index; d->stripes.stripe_count = stripe_count; d->stripes.owned_rows = owned;
+	// rasteriser units: 32 x 32 pixels for a whole frame, wider and flatter the smaller the share of the rows (raster.cuh)
+	d->raster.tile_shift_x = d->raster2.tile_shift_x = d->raster_tile_shift ? d->raster_tile_shift : (stripe_count >= 4u ? 7u : stripe_count >= 2u ? 6u : 5u);
 	d->stripes.h_shift = 0xFFFFFFFFu;
 	for (uint32_t k = 0; k != 32u; ++k) if (stripe_height == (1u << k)) d->stripes.h_shift = k;
 	size_t pixels = (size_t) owned * width;

@@ -23,12 +23,15 @@
 namespace RL_NS {
 
 #define RL_RASTER_SMALL 48u            // largest bounding box (pixels) that the setup thread rasterises itself
-#define RL_RASTER_TILE 32u             // a unit of raster_tiles_kernel is RL_RASTER_TILE^2 pixels = 32 blocks of 8x4, one per lane
+// A unit of raster_tiles_kernel is 1024 pixels = 32 blocks of 8x4, one per lane: 2^tile_shift_x pixels wide and
+// 2^(10 - tile_shift_x) of the device's LOCAL rows high. 32 x 32 when the device owns every row; a device that owns every
+// N-th stripe sees triangles squeezed to 1 / N of their height in its row space, where wide, flat units (128 x 8) cover them
+// with fewer units (the per-unit chain -- ticket, item search, classification -- is what the kernel costs at small shares).
 #define RL_RASTER_MAX_ITEMS (1u << 20) // queued triangles; scenes with more triangles than that use the BVH walk (api.cu)
 
 struct __align__(16) RasterItem {
 	uint32_t tri, first_unit;      // slot in SceneView::tris; number of this triangle's first unit
-	uint16_t tx0, ty0, ntx, nty;   // its tiles: origin and counts, in units of RL_RASTER_TILE pixels
+	uint16_t tx0, ty0, ntx, nty;   // its tiles: origin and counts, in tiles
 	float fu[3], fv[3], fw[3];     // the three edge functions A px + B py + C (>= 0 inside, scaled by det > 0)
 	float slack[3];                // bound on their evaluation error anywhere on the screen
 };
@@ -38,6 +41,7 @@ struct RasterBuffers {
 	RasterItem* items;
 	unsigned long long* counter;     // {items << 32 | units}, bumped by one atomic per queued triangle
 	unsigned int* ticket;            // next unit of raster_tiles_kernel
+	uint32_t tile_shift_x;           // log2 of the unit width in pixels, 5 .. 8 (the unit height is 2^(10 - tile_shift_x) local rows)
 };
 
 // slack[k]: 1e-4 of the magnitudes of the terms that function k is summed from, anywhere on the screen -- hundreds of ulps of
@@ -180,8 +184,9 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(SceneView s, FrameUni
 	const float K = early_z_constant(sv, g_det);
 	bool inline_raster = w * h <= RL_RASTER_SMALL;
 	if (!inline_raster) {
-		const uint32_t tx0 = (uint32_t) x0 / RL_RASTER_TILE, ty0 = l0 / RL_RASTER_TILE;
-		const uint32_t ntx = (uint32_t) x1 / RL_RASTER_TILE - tx0 + 1u, nty = (l_end - 1u) / RL_RASTER_TILE - ty0 + 1u;
+		const uint32_t sx = rb.tile_shift_x, sy = 10u - sx;
+		const uint32_t tx0 = (uint32_t) x0 >> sx, ty0 = l0 >> sy;
+		const uint32_t ntx = ((uint32_t) x1 >> sx) - tx0 + 1u, nty = ((l_end - 1u) >> sy) - ty0 + 1u;
 		const unsigned long long old = atomicAdd(rb.counter, (1ull << 32) + (unsigned long long) (ntx * nty));
 		const uint32_t index = (uint32_t) (old >> 32);
 		if (index < RL_RASTER_MAX_ITEMS) {
@@ -213,6 +218,7 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 	// consecutive units mostly belong to the same triangle, whose item search and loads are then done once per chunk. The next
 	// ticket is claimed before the current chunk is processed so that the atomic's round trip overlaps the pixel tests.
 	const uint32_t chunk = min(8u, max(1u, unit_count / (gridDim.x * 4u * 16u)));
+	const uint32_t sx = rb.tile_shift_x, sy = 10u - sx, across_shift = sx - 3u, across_mask = (1u << across_shift) - 1u;
 	uint32_t next_base = 0;
 	if (lane == 0) next_base = atomicAdd(rb.ticket, chunk);
 	next_base = __shfl_sync(0xFFFFFFFFu, next_base, 0);
@@ -242,25 +248,25 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 					cross3(mk3(tri.e2.x, tri.e2.y, tri.e2.z), mk3(tri.e1.x, tri.e1.y, tri.e1.z)));
 			}
 			const uint32_t local = unit - it.first_unit;
-			// tiles are RL_RASTER_TILE pixels wide and RL_RASTER_TILE of this device's LOCAL rows high
+			// tiles are 2^sx pixels wide and 2^sy of this device's LOCAL rows high
 			// local / ntx without an integer division (5.6 % of the kernel's instructions): local < 2^20 and ntx <= 2^10, so the
 			// product with the approximate reciprocal is off by < 2.5e-4 while (local + 0.5) / ntx stays 0.5 / ntx >= 4.9e-4 away from an integer
 			// (images beyond 32 k pixels in either direction take the division)
 			const uint32_t tile_j = (it.ntx <= 1024u && it.nty <= 1024u) ? (uint32_t) (((float) local + 0.5f) * approx_rcp((float) it.ntx)) : local / it.ntx;
 			const uint32_t tile_i = local - tile_j * it.ntx;
-			const uint32_t tile_x = (it.tx0 + tile_i) * RL_RASTER_TILE, tile_row = (it.ty0 + tile_j) * RL_RASTER_TILE;
-			const float tx1 = (float) min(tile_x + RL_RASTER_TILE, f.width) - 1.0f;
-			const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + RL_RASTER_TILE, st.owned_rows) - 1u);
+			const uint32_t tile_x = (it.tx0 + tile_i) << sx, tile_row = (it.ty0 + tile_j) << sy;
+			const float tx1 = (float) min(tile_x + (1u << sx), f.width) - 1.0f;
+			const float ty0 = (float) st.global_row(tile_row), ty1 = (float) st.global_row(min(tile_row + (1u << sy), st.owned_rows) - 1u);
 			if (rect_rejected(ef, (float) tile_x, ty0, tx1, ty1)) continue;
-			// 32 blocks of 8x4 pixels (4 across, 8 down), classified one per lane
-			const uint32_t bx = tile_x + (lane & 3u) * 8u, brow = tile_row + (lane >> 2) * 4u;
+			// 32 blocks of 8x4 pixels (2^(sx - 3) across), classified one per lane
+			const uint32_t bx = tile_x + (lane & across_mask) * 8u, brow = tile_row + (lane >> across_shift) * 4u;
 			bool live = bx < f.width && brow < st.owned_rows;
 			if (live) live = !rect_rejected(ef, (float) bx, (float) st.global_row(brow), (float) min(bx + 7u, f.width - 1u), (float) st.global_row(min(brow + 3u, st.owned_rows - 1u)));
 			unsigned todo = __ballot_sync(0xFFFFFFFFu, live);
 			while (todo) {
 				const uint32_t b = (uint32_t) __ffs(todo) - 1u;
 				todo &= todo - 1u;
-				const uint32_t x = tile_x + (b & 3u) * 8u + (lane & 7u), row = tile_row + (b >> 2) * 4u + (lane >> 3);
+				const uint32_t x = tile_x + (b & across_mask) * 8u + (lane & 7u), row = tile_row + (b >> across_shift) * 4u + (lane >> 3);
 				if (x < f.width && row < st.owned_rows) raster_pixel(f, rf, tri, ef, K, x, st.global_row(row), row * f.width + x, rb.zbuf);
 			}
 		}

@@ -331,8 +331,18 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
     dev.traversal_counters(True)
     resident_step(False)
     trav = dev.traversal_counters(False)
+    # ---- the collective alone: one gather of the slabs as they are, between events on the library's stream (after a barrier, so
+    # that no rank's wait for another rank's frames is counted)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        g0.record(stream)
+        gat.gather()
+        g1.record(stream)
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
     t = torch.tensor([ms, float(counters["shaded_pixels"]), float(counters["candidates"]), float(counters["shadow_rays"]), float(launches)] + list(pass_ms)
-                     + [float(trav["rays"]), float(trav["node_visits"]), float(trav["triangle_tests"]), float(trav["occluded"])],
+                     + [float(trav["rays"]), float(trav["node_visits"]), float(trav["triangle_tests"]), float(trav["occluded"]), gather_ms],
                      dtype=torch.float64, device=f"cuda:{local}")
     tmax = t.clone()
     if world > 1:
@@ -408,7 +418,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
                               hbm_bytes_per_ray=RAY_RECORD_BYTES, hbm_frac=(RAY_RECORD_BYTES * rays / trace_s / 1e9 / hbm_peak) if rays and trace_s > 0 else None,
                               traffic=hw.get("trace_dram_bytes_per_launch"),
                               note="achieved = (node visits x 64 B + triangle tests x 48 B + 48 B ray record) x rays / kernel time: bytes the kernel requests from L1/L2, of which only the ray records (hbm_bytes_per_ray) must come from HBM")
-        kernels = dict(per_step, shade_ms=shade_ms, shadow_rays_per_step=float(t[3]), shaded_pixel_samples_per_step=shaded, note=breakdown_note)
+        kernels = dict(per_step, shade_ms=shade_ms, gather_ms=float(tmax[15]), shadow_rays_per_step=float(t[3]), shaded_pixel_samples_per_step=shaded, note=breakdown_note)
         per_device_mb = (W * H // world) * 140 / 2 ** 20      # visibility, pick, origin, base, group, two ray slots, accumulation
         line = dict(metric="shaded light-samples/sec", value=value, unit="Gsamples/s", n_gpus=world, steps=steps, warmup=args.warmup,
                     ms_per_step=ms_max / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",

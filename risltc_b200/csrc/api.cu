@@ -588,7 +588,7 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 	const bool defer = deferred_rays(v);
 	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
 		&& v.mis_heuristic == MIS_OPTIMAL_CLAMPED && v.sample_count == 1u && v.light_samples == 1u && v.fast_atan == 0u
-		&& (v.max_light_vertices == 3u || v.max_light_vertices == 4u) && v.min_light_vertices == v.max_light_vertices
+		&& ((v.max_light_vertices == 3u && v.min_light_vertices == 3u) || (v.max_light_vertices == 4u && v.min_light_vertices >= 3u))
 		&& d->view.light_stride4 == 3u + v.max_light_vertices && d->view.lights_tri != nullptr;
 	if (specialised) {
 		const bool quads = v.max_light_vertices == 4u;
@@ -618,11 +618,11 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 			const uint32_t threads = d->winner_threads, per_cta = threads / 32;
 			uint32_t wctas = 2u * (uint32_t) d->sm_count;
 			if (wctas * per_cta > tile_count) wctas = (tile_count + per_cta - 1) / per_cta;
-			if (quads) winner_kernel<384, 768, 4><<<std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			if (quads) winner_kernel<384, 768, 4><<<std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count, v.min_light_vertices);
 			else if (d->winner_cr) { if (rl_launch_winner_cr(d->view, f, d->stripes, px, tiles_x, tile_count, std::min(2u * (uint32_t) d->sm_count, (tile_count + 11u) / 12u), stream)) return 1; }
-			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else if (threads == 320) winner_kernel<320, 640><<<wctas, 320, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
-			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
+			else if (threads == 256) winner_kernel<256, 512><<<wctas, 256, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count, 3u);
+			else if (threads == 320) winner_kernel<320, 640><<<wctas, 320, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count, 3u);
+			else winner_kernel<384, 768><<<wctas, 384, 0, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count, 3u);
 		}
 		d->launches += 1;
 	}

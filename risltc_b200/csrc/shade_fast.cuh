@@ -282,8 +282,10 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc3_kernel(Sce
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The same kernel for QUAD lights (every light has four vertices: MIN = MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 4, the shape
-// polygonal_light.c creates by default and the V = 4 variants of the comparison matrix use). What changes is the size of
+// The same kernel for QUAD lights (MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 4, the shape polygonal_light.c creates by default and the
+// V = 4 variants of the comparison matrix use). Triangles among them are fine: write_lights repeats a light's first vertex up
+// to the maximal count (main.c:483-487), and a quad {v0, v1, v2, v0} has the triangle's form factor (the extra edges have
+// zero length: their cross products are exactly 0) and the triangle's clipped polygon. What changes is the size of
 // things: table records {v0 | Le.r, v1 | Le.g, v2 | Le.b, v3 | 0}, a four-edge form factor, and the horizon clip of a quad
 // (up to five vertices, rare: a small walk through local arrays). Strides are chosen ODD in 16-byte units, so that
 // consecutive slots / random records spread over all eight 16-byte bank groups like the triangle kernel's 48-byte records
@@ -517,14 +519,15 @@ __device__ __forceinline__ uint32_t clip_triangle_to_horizon(float3 (&v)[4]) {
 // (496-byte frames x 768 threads = 380 KB per SM, more than L1 holds): ncu showed 48 M + 47 M local sectors per launch and
 // 477 MB of DRAM writes against 232 MB algorithmic (profiles/r1_ncu_final_kernels.txt).
 // The draws keep the reference's order (diffuse pair, then specular pair only if its solid angle is positive).
-// V = vertices of every light (3: triangles, the bench configurations; 4: quads, the reference's default light shape --
-// the clipped polygon then has up to P = V + 1 vertices and the clip is the generic rotation-table walk of shading.cuh).
+// V = MAX_POLYGONAL_LIGHT_VERTEX_COUNT (3: triangles, the bench configurations; 4: quads, the reference's default light
+// shape, or a mix of triangles and quads -- the clipped polygon then has up to P = V + 1 vertices and the clip is the generic
+// rotation-table walk of shading.cuh, which takes the light's own vertex count and MIN_POLYGONAL_LIGHT_VERTEX_COUNT).
 template <int RL_WIN_THREADS, int RL_WIN_RESIDENT_THREADS, int V = 3>
-__global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count) {
+__global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_WIN_THREADS) winner_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out, uint32_t tiles_x, uint32_t tile_count, uint32_t min_light_vertices) {
 	constexpr int P = V + 1;
 	constexpr int RL_POLY_WORDS = 5 * P + 4;   // vc, v[P], e[P], inner0, sector[P], total
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = RL_WIN_THREADS / 32;
-	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, (uint32_t) V, (uint32_t) V };
+	const Variant var = { 1u, TECH_LTC_CP, MIS_OPTIMAL_CLAMPED, 1u, 1u, 0u, (V == 3) ? 3u : min_light_vertices, (uint32_t) V };
 	// a warp owns 8x4 pixel tiles; the CTA takes `warps` neighbouring tiles per round through a ticket (barriers inside)
 	__shared__ uint32_t sm_base;
 	__shared__ float sm_poly[RL_POLY_WORDS][RL_WIN_THREADS];
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 				pv[V] = mk3(0.0f, 0.0f, 0.0f);
 				uint32_t vc;
 				if (V == 3) vc = clip_triangle_to_horizon(reinterpret_cast<float3 (&)[4]>(pv));
-				else vc = clip_to_horizon<P>((uint32_t) V, pv, (uint32_t) V);
+				else vc = clip_to_horizon<P>(__float_as_uint(__ldg(light_record + 2).x), pv, var.min_light_vertices);   // the light's own vertex count (main.c:478)
 				if (tech == 0) { polygon_d = vc != 0u; live = polygon_d; }
 				if (vc != 0u) {
 					PsaPolygon<P> p;
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(RL_WIN_THREADS, RL_WIN_RESIDENT_THREADS / RL_W
 		if (live) {
 			Light<V> light;
 			const float4 la = __ldg(light_record), lb = __ldg(light_record + 1);
-			light.radiance = mk3(la.x, la.y, la.z); light.plane = lb; light.count = (uint32_t) V;
+			light.radiance = mk3(la.x, la.y, la.z); light.plane = lb; light.count = (V == 3) ? 3u : __float_as_uint(__ldg(light_record + 2).x);
 			technique_weights(t, sp, ltc.albedo, total_d, total_s, light.radiance, false);
 			const int techniques = (total_s > 0.0f) ? 2 : 1;
 			for (int j = 0; j != techniques; ++j) {

@@ -13,6 +13,6 @@ using namespace RL_NS;
 int rl_launch_winner_cr(const SceneView& s, const FrameUniforms& f, const Stripes& st, const PixelBuffers& px, uint32_t tiles_x, uint32_t tile_count,
 	uint32_t ctas, cudaStream_t stream)
 {
-	winner_kernel<384, 768><<<ctas, 384, 0, stream>>>(s, f, st, px, tiles_x, tile_count);
+	winner_kernel<384, 768><<<ctas, 384, 0, stream>>>(s, f, st, px, tiles_x, tile_count, 3u);
 	return 0;
 }

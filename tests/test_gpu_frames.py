@@ -123,6 +123,20 @@ def test_quad_lights_on_the_specialised_kernels(device, ltc_tables, frames):
     assert counters["candidates"] == 32 * counters["shaded_pixels"]      # the counters of the specialised RIS kernel
 
 
+def test_mixed_triangle_and_quad_lights_on_the_specialised_kernels(device, ltc_tables):
+    """MIN = 3, MAX = 4 vertices: write_lights repeats a triangle's first vertex in the fourth slot (main.c:483-487), the RIS
+    kernel integrates the degenerate quad, the winner kernel clips with the light's own vertex count."""
+    from oracle import orc
+    from risltc_b200 import api, scenes
+    kw = dict(min_vertices=3, max_vertices=4)
+    scene = scenes.many_light_room(48, 60, seed=9, width=320, height=180, vertex_count=(3, 4))
+    assert sorted({len(l["vertices_plane_space"]) for l in scene["lights"]}) == [3, 4]
+    ref, ref_vis, ref_rays, got, vis, counters = _render_both(device, scene, ltc_tables, orc.variant(**kw), api.variant(**kw), 320, 180, 4, "fast")
+    assert np.array_equal(vis, ref_vis)
+    check("room 48 lights with 3 or 4 vertices 320x180, default estimator", "fast", got, ref, 4, counters, ref_rays)
+    assert counters["candidates"] == 32 * counters["shaded_pixels"]      # the counters of the specialised RIS kernel
+
+
 @pytest.mark.parametrize("precision", ["exact", "fast"])
 @pytest.mark.parametrize("lights", [1024, 4096])
 def test_many_lights(device, ltc_tables, lights, precision):

@@ -689,7 +689,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			// (1) every triangle finds its pixels and competes for them with atomicMin on {t, index} (raster.cuh)
 			raster_setup_kernel<<<(d->view.triangle_count + 127) / 128, 128, 0, stream>>>(d->view, f, d->stripes, raster);
 			raster_tiles_kernel<<<d->sm_count * 8, 128, 0, stream>>>(d->view, f, d->stripes, raster);
-			raster_resolve_kernel<<<(px.pixel_count + 255) / 256, 256, 0, stream>>>(raster.zbuf, px.visibility, px.pixel_count, raster.counter);
+			raster_resolve_kernel<<<((px.pixel_count + 3) / 4 + 255) / 256, 256, 0, stream>>>(raster.zbuf, px.visibility, px.pixel_count, raster.counter);
 			d->launches += 2;
 		}
 		else gbuffer_kernel<<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);

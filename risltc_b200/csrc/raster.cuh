@@ -275,14 +275,27 @@ __global__ void __launch_bounds__(128) raster_tiles_kernel(SceneView s, FrameUni
 
 // Keys -> ids; the kernel also leaves the key buffer, the item counter and the unit ticket cleared for the next frame that uses
 // this set of buffers (they are cleared once when they are allocated), so that a frame needs no memset operations.
-__global__ void __launch_bounds__(256) raster_resolve_kernel(unsigned long long* zbuf, uint32_t* visibility, uint32_t pixel_count, unsigned long long* counter_and_ticket) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i == 0u) { counter_and_ticket[0] = 0ull; counter_and_ticket[1] = 0ull; }
-	if (i >= pixel_count) return;
-	const unsigned long long key = zbuf[i];
-	zbuf[i] = ~0ull;
+// Four pixels per thread with 16-byte accesses (one pixel per thread ran at a seventh of the HBM rate: 45 us for the 41 MB of a
+// 1080p frame); the tail of a buffer whose size is not a multiple of four goes one pixel at a time.
+__device__ __forceinline__ uint32_t raster_key_to_id(unsigned long long key) {
 	const uint32_t low = (uint32_t) key;
-	visibility[i] = (key == ~0ull) ? 0xFFFFFFFFu : ((low >> 1) | (low << 31));
+	return (key == ~0ull) ? 0xFFFFFFFFu : ((low >> 1) | (low << 31));
+}
+__global__ void __launch_bounds__(256) raster_resolve_kernel(unsigned long long* zbuf, uint32_t* visibility, uint32_t pixel_count, unsigned long long* counter_and_ticket) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t == 0u) { counter_and_ticket[0] = 0ull; counter_and_ticket[1] = 0ull; }
+	const uint32_t i = 4u * t;
+	if (i + 3u < pixel_count) {
+		ulonglong2* keys = (ulonglong2*) (zbuf + i);
+		const ulonglong2 a = keys[0], b = keys[1];
+		keys[0] = make_ulonglong2(~0ull, ~0ull); keys[1] = make_ulonglong2(~0ull, ~0ull);
+		*(uint4*) (visibility + i) = make_uint4(raster_key_to_id(a.x), raster_key_to_id(a.y), raster_key_to_id(b.x), raster_key_to_id(b.y));
+	}
+	else for (uint32_t k = i; k < pixel_count; ++k) {
+		const unsigned long long key = zbuf[k];
+		zbuf[k] = ~0ull;
+		visibility[k] = raster_key_to_id(key);
+	}
 }
 
 }  // namespace RL_NS

@@ -32,7 +32,7 @@ int rl_fail(const char* what, const char* detail) {
 #define RL_TRACE_CANDIDATES 3u
 #define RL_TRACE_TRIALS (2u * RL_TRACE_CANDIDATES)   // every candidate is timed on two frames (the faster counts: the first frames after an upload run on cold caches)
 #define RL_TRACE_DECIDED (RL_TRACE_TRIALS + 1u)
-// auto: scenes from 8 M triangles on are built on the device. Measured on B200 (gpurun_out/wl_*_bvh_*.json, round 2): 5 M triangles
+// auto: scenes from 8 M triangles on are built on the device. Measured on B200: 5 M triangles
 // (C4) build in 7-8 s on the host and in 24 ms on the device (PLOC; 14.6 ms of kernels). The clustered tree is as good as the
 // SAH tree for shadow rays (C2 -3 %, C3 +3 %, C4 +9 % kernel time) but costs the per-pixel BVH walk of C4 +40 %: a scene is
 // built once and rendered for thousands of frames, so the host's binned-SAH tree stays the default until its build takes ~10 s.
@@ -434,7 +434,7 @@ static int allocate_ray_buffers(risltc_device_t* d) {
 	return 0;
 }
 
-// Measured on B200 with the round-2 kernels (bench.py, RISLTC_OVERLAP=0|1; gpurun_out/ov_*.json): overlapping frames wins
+// Measured on B200 with the round-2 kernels (bench.py, RISLTC_OVERLAP=0|1): overlapping frames wins
 // 5-7 % on a whole 1080p frame (C2 33.0 -> 34.6, C4 17.2 -> 18.4 Gsamples/s), 9 % on half of one, 9-19 % on an eighth (the
 // tails of the persistent kernels are then a fifth of a frame's time), 2 % on half a 4K frame (4.1 M pixels) and nothing on
 // a whole 4K frame (8.3 M pixels), where the second set of per-frame buffers (140 bytes per pixel) is not worth its memory

@@ -67,7 +67,7 @@ struct risltc_device_s {
 	cudaEvent_t ev_resolved[2] = { nullptr, nullptr }, ev_fork = nullptr, ev_join = nullptr;
 	uint32_t last_set = 0;
 	uint32_t precision = RISLTC_PRECISION_FAST;
-	int sm_count = 148, trace_resident = 1, trace4_resident = 1, trace4p_resident = 1;
+	int sm_count = 148, trace_resident = 1, trace4_resident = 1, trace4p_resident = 1, trace4pu_resident = 1;   // CTAs per SM of the shadow-ray kernels (pu: pairs, unordered)
 	int trace_ctas_per_sm = 0;   // 0: as many as fit
 	uint32_t refill = 4;   // idle lanes that trigger a refill of the warp from its staged rays (sweep with the pair kernel, round 2: 1 / 2 / 4 / 6 / 10 -> C2 trace -- / 10.19 / 10.08 / 10.18 / 10.49 ms, C3 231.4 / 226.8 / 226.8 / 229.7 / 239.2 ms; RISLTC_REFILL)
 	// (1) has two bit-identical implementations: 1 = triangle-parallel rasteriser (raster.cuh; wins when few triangles cover
@@ -157,6 +157,7 @@ extern "C" int risltc_cuda_create_device(risltc_device_t** device, int cuda_ordi
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace_resident, trace_kernel, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4_resident, trace4_kernel<false>, 128, 0));
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4p_resident, trace4p_kernel<false>, 128, 0));
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d->trace4pu_resident, trace4p_kernel<false, false>, 128, 0));
 	if (const char* e = getenv("RISLTC_TRI_VOTE")) { d->tri_vote = (uint32_t) atoi(e); d->trace_pinned = true; d->trace_tune = RL_TRACE_DECIDED; }   // tuning knobs
 	if (const char* e = getenv("RISLTC_TRACE_ORDERED")) { d->trace_ordered = atoi(e) != 0; d->trace_pinned = true; d->trace_tune = RL_TRACE_DECIDED; }
 	for (auto& ev : d->trace_tune_ev) CU(cudaEventCreate(&ev));
@@ -701,8 +702,7 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 		if (traced) {
 			// (3) persistent any-hit traversal over all ray slots
 			const uint32_t ray_count = px.pixel_count * d->variant.light_samples * d->variant.sample_count * 2u;
-			const int resident = (d->trace_kind == 8) ? d->trace4p_resident : d->trace4_resident;
-			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < resident) ? d->trace_ctas_per_sm : resident;
+			int resident = (d->trace_kind == 8) ? d->trace4p_resident : d->trace4_resident;
 			// candidates: {triangle-track threshold, nearest child first}; the first is the default and wins ties (3 %)
 			static const uint32_t vote_candidates[RL_TRACE_CANDIDATES] = { 8u, 1u, 8u };
 			static const bool order_candidates[RL_TRACE_CANDIDATES] = { true, true, false };
@@ -722,6 +722,8 @@ extern "C" int risltc_cuda_render_frames(risltc_device_t* d, const void* blocks,
 			const uint32_t tuning = d->trace_tune;
 			if (tuning < RL_TRACE_TRIALS) { d->tri_vote = vote_candidates[tuning % RL_TRACE_CANDIDATES]; d->trace_ordered = order_candidates[tuning % RL_TRACE_CANDIDATES]; CU(cudaEventRecord(d->trace_tune_ev[2 * tuning], stream)); }
 			const bool ordered = d->trace_ordered || d->trace_kind != 8;
+			if (!ordered) resident = d->trace4pu_resident;   // the unordered variant needs fewer registers: one more CTA per SM
+			const int per_sm = (d->trace_ctas_per_sm > 0 && d->trace_ctas_per_sm < resident) ? d->trace_ctas_per_sm : resident;
 			if (d->trace_kind == 8 && d->count_traversal && ordered) trace4p_kernel<true, true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 8 && d->count_traversal) trace4p_kernel<true, false><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);
 			else if (d->trace_kind == 8 && ordered) trace4p_kernel<false, true><<<d->sm_count * per_sm, 128, 0, stream>>>(d->view, px, ray_count / 2u, d->tri_vote, d->refill, 0x3F800000u);

@@ -116,6 +116,7 @@ def make_workload(name, lights=None):
 ESTIMATORS = {
     "uniform_uniform": ("uniform", "area_turk"), "uniform_cp": ("uniform", "projected_solid_angle"), "uniform_area": ("reservoir", "area_turk"),
     "cp_cp": ("reservoir", "projected_solid_angle"), "ltc_cp": ("reservoir", "ltc_cp"),
+    "uniform_ltc_cp": ("uniform", "ltc_cp"),   # not in the timing experiment: our estimator without the reservoir (specialised kernels, too)
 }
 ESTIMATOR = "ltc_cp"
 LIGHT_VERTICES = 0  # --light-vertices 4: quad lights instead of the workload's triangles (reference variant ris_ltc_v4)
@@ -423,7 +424,7 @@ def measure(args, wl, rank, world, local, want_cpu, same_workload_one_gpu=False)
         line = dict(metric="shaded light-samples/sec", value=value, unit="Gsamples/s", n_gpus=world, steps=steps, warmup=args.warmup,
                     ms_per_step=ms_max / steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=wl["desc"], variant=("light_reservoir (m=32) + sample_polygon_ltc_cp + mis_optimal_clamped, S=1, L=1" if fast_path else "light_uniform + projected_solid_angle" if wl["name"] == "c1"
-                                                            else f"timing-experiment estimator {ESTIMATOR}: light_{ESTIMATORS[ESTIMATOR][0]} + sample_polygon_{ESTIMATORS[ESTIMATOR][1]} (generic kernel)"),
+                                                            else f"timing-experiment estimator {ESTIMATOR}: light_{ESTIMATORS[ESTIMATOR][0]} + sample_polygon_{ESTIMATORS[ESTIMATOR][1]} ({'specialised pick + winner kernels' if ESTIMATOR == 'uniform_ltc_cp' else 'generic kernel'})"),
                                 lights=wl["lights"], triangles=triangles, width=W, height=H, spp=spp,
                                 acceleration_structure=dict(builder=bvh["builder"], build_ms=round(bvh["build_ms"], 1), device_ms=[round(x, 2) for x in bvh["device_ms"]],
                                                             wide_nodes=bvh["wide_nodes"], depth=[bvh["binary_depth"], bvh["wide_depth"]],

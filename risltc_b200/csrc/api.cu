@@ -587,7 +587,7 @@ static const uint32_t kMaxSmemLights = 2048;
 static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, const PixelBuffers& px, cudaStream_t stream, cudaEvent_t between) {
 	const Variant& v = d->variant;
 	const bool defer = deferred_rays(v);
-	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling == 1u && v.polygon_technique == TECH_LTC_CP
+	const bool specialised = d->precision == RISLTC_PRECISION_FAST && v.light_sampling <= 1u && v.polygon_technique == TECH_LTC_CP
 		&& v.mis_heuristic == MIS_OPTIMAL_CLAMPED && v.sample_count == 1u && v.light_samples == 1u && v.fast_atan == 0u
 		&& ((v.max_light_vertices == 3u && v.min_light_vertices == 3u) || (v.max_light_vertices == 4u && v.min_light_vertices >= 3u))
 		&& d->view.light_stride4 == 3u + v.max_light_vertices && d->view.lights_tri != nullptr;
@@ -606,7 +606,12 @@ static int launch_shade(risltc_device_t* d, dim3 grid, const FrameUniforms& f, c
 		uint32_t ctas = (uint32_t) d->sm_count;
 		if (ctas * warps > tile_count) ctas = (tile_count + warps - 1) / warps;
 		const bool textured = d->view.textures != nullptr;
-		if (quads) {
+		if (v.light_sampling == 0u) {
+			// light_uniform: no candidates, one uniform draw per pixel (shade_fast.cuh)
+			if (textured) pick_uniform_kernel<true><<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);
+			else pick_uniform_kernel<false><<<grid, 128, 0, stream>>>(d->view, f, d->stripes, px);
+		}
+		else if (quads) {
 			if (smem && !textured) ris_ltc4_kernel<true, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else if (!textured) ris_ltc4_kernel<false, false><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);
 			else if (smem) ris_ltc4_kernel<true, true><<<ctas, 32 * warps, bytes, stream>>>(d->view, f, d->stripes, px, tiles_x, tile_count);

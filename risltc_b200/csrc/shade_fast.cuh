@@ -486,6 +486,45 @@ __global__ void __launch_bounds__(32 * RL_FAST_MAX_WARPS, 1) ris_ltc4_kernel(Sce
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// light_uniform + sample_polygon_ltc_cp (shading_pass.frag.glsl:707-721 with :292-397): no reservoir -- the light is one
+// uniform draw and the estimate is N times the same estimator that the RIS winner gets. This kernel is kernel 2a without
+// its candidates: G-buffer decode, LTC lookup, the draw, and the hand-over records (pick = {light, W = N, RNG state},
+// shading point) that winner_kernel, the shadow-ray kernel and resolve_kernel continue from. One thread per pixel.
+template <bool TEXTURED>
+__global__ void __launch_bounds__(128) pick_uniform_kernel(SceneView s, FrameUniforms f, Stripes st, PixelBuffers out) {
+	uint32_t x, row, y;
+	if (!tile_pixel(f, st, x, row, y)) return;
+	const uint32_t pixel = row * f.width + x;
+	const uint32_t prim = out.visibility[pixel];
+	const bool active = prim != 0xFFFFFFFFu && (prim >> 31) == 0u;
+	if (!active) {
+		const float v = (prim == 0xFFFFFFFFu) ? 0.0f : 1.0f;
+		out.base[pixel] = make_float4(v, v, v, (prim == 0xFFFFFFFFu) ? 1.0f : 0.0f);
+		out.origin[pixel] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+		return;
+	}
+	const ShadingPoint sp = reconstruct_shading_point<TEXTURED>(s, f, prim, primary_ray(f, x, y));
+	const float fresnel_luminance = dot3(sp.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
+	const LtcFrame ltc = make_ltc_frame(s, fresnel_luminance, sp.roughness, sp.position, sp.normal, sp.outgoing, f.ltc_constants);
+	uint32_t seed = noise_seed(x, y, f.width, f.frame_word);
+	const size_t n = out.pixel_count;
+	out.shade[pixel] = make_float4(sp.position.x, sp.position.y, sp.position.z, sp.roughness);
+	out.shade[n + pixel] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, ltc.s00);
+	out.shade[2 * n + pixel] = make_float4(sp.diffuse_albedo.x, sp.diffuse_albedo.y, sp.diffuse_albedo.z, -ltc.s20);
+	out.shade[3 * n + pixel] = make_float4(sp.fresnel_0.x, sp.fresnel_0.y, sp.fresnel_0.z, ltc.s11);
+	out.shade[4 * n + pixel] = make_float4(sp.outgoing.x, sp.outgoing.y, sp.outgoing.z, ltc.s02);
+	out.shade[5 * n + pixel] = make_float4(ltc.s22, ltc.albedo, 0.0f, 0.0f);
+	// light_idx = int(get_noise_1() * N), clamped (the draw can round to 1.0)
+	const int N = (int) s.light_count;
+	seed = 1664525u * seed + 1013904223u;
+	const int idx = min((int) (__uint2float_rn(seed) * ((float) N * 2.3283064365386962890625e-10f)), N - 1);
+	out.pick[pixel] = make_uint4((uint32_t) idx, __float_as_uint((float) N), seed, 0u);
+	const unsigned active_mask = __activemask();
+	const unsigned total = (unsigned) __popc(active_mask);
+	if ((threadIdx.x & 31u) == (unsigned) (__ffs(active_mask) - 1)) atomicAdd(&out.counters[0], (unsigned long long) total);
+}
+
 // clip_to_horizon<4> for a triangle (vertex count == MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING == 3) without the dynamically
 // indexed walk: the same vertices in the same order (polygon_clipping.glsl:56-75: row 0 of the rotation table), every slot
 // addressed statically so that the polygon stays in registers. horizon_crossing(v_i, v_i+1) per crossed edge, as there.

@@ -220,6 +220,10 @@ int risltc_cuda_check_bvh(const float* vertices, uint64_t triangle_count, uint32
 /* The same report for the acceleration structures upload_scene left on the device, whichever builder made them; report[0]
  * additionally counts triangle records that are not bit-identical to {v0, v1 - v0, v2 - v0, id} of their triangle. */
 int risltc_cuda_check_scene_bvh(risltc_device_t* device, uint64_t report[6]);
+/* Host-only: a hash of everything the host builder produces for these triangles (binary tree, triangle order, 4-wide tree).
+ * The builder splits the top levels of large scenes over tasks; RISLTC_BVH_THREADS=1 keeps it on the calling thread -- the
+ * trees, and this hash, are the same. */
+int risltc_cuda_bvh_checksum(const float* vertices, uint64_t triangle_count, uint32_t max_leaf, uint64_t* checksum);
 
 #ifdef __cplusplus
 }

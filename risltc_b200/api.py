@@ -71,6 +71,14 @@ def check_bvh(vertices, max_leaf=2):
     return dict(bad_order=r[0], bad_binary=r[1], bad_wide=r[2], binary_nodes=r[3], wide_nodes=r[4], depth=r[5] >> 32, children_per_node=(r[5] & 0xFFFFFFFF) / 100.0)
 
 
+def bvh_checksum(vertices, max_leaf=2):
+    """Host-only hash of the host builder's output for these triangles ([T, 3, 3] float32)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 9)
+    out = C.c_uint64()
+    _check(lib().risltc_cuda_bvh_checksum(_p(v), C.c_uint64(v.shape[0]), C.c_uint32(max_leaf), C.byref(out)))
+    return int(out.value)
+
+
 class Device:
     """One risltc_device_t: one CUDA device, one stream, one image stripe set."""
 

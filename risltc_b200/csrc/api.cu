@@ -961,6 +961,20 @@ extern "C" int risltc_cuda_check_bvh(const float* vertices, uint64_t T, uint32_t
 	return 0;
 }
 
+// FNV-1a over the host builder's binary tree, triangle order and 4-wide tree: equal for equal trees (host-only)
+extern "C" int risltc_cuda_bvh_checksum(const float* vertices, uint64_t T, uint32_t max_leaf, uint64_t* checksum) {
+	if (!vertices || T == 0 || !checksum) return fail("bvh_checksum: no triangles", nullptr);
+	std::vector<BvhNodeHost> nodes; std::vector<uint32_t> order;
+	build_bvh(vertices, T, nodes, order, max_leaf);
+	std::vector<Qbvh4NodeHost> n4;
+	build_qbvh4(nodes, n4);
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&](const void* data, size_t bytes) { const unsigned char* p = (const unsigned char*) data; for (size_t i = 0; i != bytes; ++i) { h ^= p[i]; h *= 1099511628211ull; } };
+	mix(nodes.data(), nodes.size() * sizeof(BvhNodeHost)); mix(order.data(), order.size() * sizeof(uint32_t)); mix(n4.data(), n4.size() * sizeof(Qbvh4NodeHost));
+	*checksum = h;
+	return 0;
+}
+
 // The same invariants for the structures upload_scene left on the device (whichever builder made them)
 extern "C" int risltc_cuda_check_scene_bvh(risltc_device_t* d, uint64_t report[6]) {
 	if (use(d)) return 1;

@@ -248,3 +248,19 @@ def test_acceleration_structures_hold_their_invariants(max_leaf):
         assert r["bad_order"] == 0 and r["bad_binary"] == 0 and r["bad_wide"] == 0, r
         assert r["wide_nodes"] <= r["binary_nodes"] and 1.0 <= r["children_per_node"] <= 4.0
         assert 3 * r["depth"] + 1 <= 88      # the traversal stack of trace4_kernel (RL_T4_OVERFLOW)
+
+
+def test_host_builder_is_the_same_tree_on_one_thread_and_on_many(monkeypatch):
+    """The host builder hands the two subtrees of the top levels of a large scene to two tasks and splices their nodes in
+    preorder (bvh_build.cpp): binary tree, triangle order and 4-wide tree are byte for byte those of the one-thread build."""
+    from risltc_b200 import api
+    rng = np.random.default_rng(5)
+    T = 260_000      # above the 100 k triangles from which subtrees are built by tasks of their own
+    soup = (rng.uniform(-20, 20, (T, 1, 3)) + rng.normal(size=(T, 3, 3)) * rng.uniform(0.01, 0.4, (T, 1, 1))).astype(np.float32)
+    monkeypatch.setenv("RISLTC_BVH_THREADS", "1")
+    one = api.bvh_checksum(soup)
+    monkeypatch.delenv("RISLTC_BVH_THREADS")
+    many = api.bvh_checksum(soup)
+    assert one == many
+    r = api.check_bvh(soup[:120_000], 2)
+    assert r["bad_order"] == 0 and r["bad_binary"] == 0 and r["bad_wide"] == 0

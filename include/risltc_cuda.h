@@ -93,7 +93,7 @@ int risltc_cuda_set_variant(risltc_device_t* device, const risltc_variant_t* var
 int risltc_cuda_set_precision(risltc_device_t* device, uint32_t mode);
 
 /* Builder of the acceleration structures (create_acceleration_structure, scene.c:142-406, where the driver builds on the
- * device): HOST = binned SAH on one host thread (~1.5 us per triangle: 7-8 s for 5 M triangles), DEVICE = built by kernels
+ * device): HOST = binned SAH, the top levels split over tasks (5 M triangles: 2.7 s on 16 cores, 7-8 s on one), DEVICE = built by kernels
  * (bvh_gpu.cu): Morton order + PLOC clustering, 5 M triangles in 24 ms; shadow rays cost -3 .. +9 % against the SAH tree,
  * the per-pixel BVH walk of huge scenes +40 %; DEVICE_RADIX = the plain radix tree over the Morton order (13 ms, shadow
  * rays 1.2-1.5x costlier). AUTO (default) = DEVICE from 8 M triangles on. Takes effect at the next upload_scene; images do
